@@ -1,0 +1,119 @@
+/*
+ * rpt_b200.h — C ABI of the B200 (sm_100a) tracing backend.
+ *
+ * This is the boundary that replaces the reference's wgpu / gpgpu-rs compute dispatch inside
+ * `trace_gpu` (src/trace.rs:136-224).  One context drives one GPU (one process per GPU); every
+ * entry point takes plain pointers and sizes, copies what it is given (the caller keeps
+ * ownership), returns an RPT_* status (rpt_errors.h) and never unwinds across the boundary.
+ * There is NO CPU fallback: without a CUDA device `rpt_create` fails with RPT_ERR_NO_DEVICE.
+ *
+ * Reference call -> replacement
+ *   gpgpu::Framework (lazy_static FW, src/trace.rs:3-5,25-38)            -> rpt_create / rpt_destroy
+ *   World::into_gpu: GpuBuffer::from_slice x5 + atlas GpuConstImage
+ *     (src/asset.rs:226-235, src/bvh.rs:40-43), skybox GpuConstImage
+ *     (src/asset.rs:257-281, src/trace.rs:144)                            -> rpt_upload_world
+ *   GpuUniformBuffer::from_slice / config_buffer.write
+ *     (src/trace.rs:168,219)                                              -> rpt_set_config
+ *   GpuBuffer::from_slice(rng) / rng_buffer.write (src/trace.rs:169,221)  -> rpt_write_rng
+ *   GpuBuffer::from_slice(output) / output_buffer.write
+ *     (src/trace.rs:170,220)                                              -> rpt_write_output
+ *   Shader/DescriptorSet/Program/Kernel::new (src/trace.rs:97-122)        -> (inside rpt_upload_world)
+ *   `for _ in 0..sync_rate { kernel.enqueue(w/8,h/8,1); FW.poll_blocking() }`
+ *     (src/trace.rs:182-193)                                              -> rpt_enqueue(n) + rpt_sync
+ *   output_buffer.read_blocking + `/ sample_count` (src/trace.rs:198-204) -> rpt_read_output /
+ *                                                                            rpt_read_framebuffer
+ *
+ * Semantics kept from the reference kernel (kernels/src/lib.rs:189-227): one "sample" advances
+ * EVERY pixel of this context's partition by one sample index — output[i] += (radiance, 1) and
+ * rng[i] = (x + 1, y).  rpt_enqueue(n) is n such samples, batched on the device.
+ */
+#ifndef RPT_B200_H
+#define RPT_B200_H
+
+#include "rpt_errors.h"
+#include "rpt_shared_structs.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rpt_context rpt_context;
+
+/* How rpt_enqueue runs the loop.  WAVEFRONT is the product path; MEGAKERNEL is the 1:1
+ * one-thread-per-pixel form of the reference kernel (binary BVH, reference traversal order),
+ * kept as the bit-exact comparison arm. */
+enum { RPT_PIPELINE_WAVEFRONT = 0, RPT_PIPELINE_MEGAKERNEL = 1 };
+
+/* Device counters accumulated since the last rpt_reset_counters (all in units of rays/paths). */
+typedef struct RptCounters {
+    uint64_t paths;        /* pixel-samples finished */
+    uint64_t nearest_rays; /* intersect_nearest calls (primary + bounce rays) */
+    uint64_t any_rays;     /* intersect_any calls (shadow rays) */
+    uint64_t kernel_launches;
+} RptCounters;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+int rpt_create(int device_id, rpt_context** out_ctx);
+int rpt_destroy(rpt_context* ctx);
+/* Message of the last failure on this context ("" if none).  ctx == NULL: last rpt_create failure. */
+const char* rpt_last_error(const rpt_context* ctx);
+int rpt_set_pipeline(rpt_context* ctx, int pipeline);
+/* Tunable: path slots kept in flight per wave of the wavefront pipeline (0 = default). */
+int rpt_set_wave_slots(rpt_context* ctx, uint32_t slots);
+
+/* ---- scene ----------------------------------------------------------------------------- */
+/* Host pointers; the library copies and re-lays-out (wide BVH, triangle streams) privately.
+ * atlas_rgba8 may be NULL (no textured material); sky_rgba32f may be NULL (2x2 magenta
+ * fallback, src/asset.rs:275-281).  lights must hold >= 1 entry (sentinel allowed). */
+int rpt_upload_world(rpt_context* ctx,
+                     const RptPerVertexData* vertices, uint32_t nvertices,
+                     const uint32_t* triangles_xyzw, uint32_t ntriangles,
+                     const RptBVHNode* nodes, uint32_t nnodes,
+                     const RptMaterialData* materials, uint32_t nmaterials,
+                     const RptLightPickEntry* lights, uint32_t nlights,
+                     const uint8_t* atlas_rgba8, uint32_t atlas_w, uint32_t atlas_h,
+                     const float* sky_rgba32f, uint32_t sky_w, uint32_t sky_h);
+
+/* ---- per-render state ------------------------------------------------------------------ */
+/* (Re)allocates rng/output when width*height changes; validates the RNG dimension budget. */
+int rpt_set_config(rpt_context* ctx, const RptTracingConfig* config);
+int rpt_write_rng(rpt_context* ctx, const uint32_t* seeds_xy, size_t npixels);
+int rpt_read_rng(rpt_context* ctx, uint32_t* seeds_xy, size_t npixels);
+/* rgba == NULL zeroes the accumulator (the flush of src/trace.rs:220). */
+int rpt_write_output(rpt_context* ctx, const float* rgba, size_t npixels);
+
+/* Multi-GPU partition of the frame.  Sample-index-range splits need no call:
+ * the host offsets seeds_xy[].x per rank.  Tile split: this context renders only pixels whose
+ * 32x32 tile index t satisfies t % tile_count == tile_rank; other pixels stay untouched. */
+int rpt_set_tile_partition(rpt_context* ctx, uint32_t tile_rank, uint32_t tile_count);
+
+/* ---- run ------------------------------------------------------------------------------- */
+int rpt_enqueue(rpt_context* ctx, uint32_t n_samples); /* asynchronous */
+int rpt_sync(rpt_context* ctx);                        /* FW.poll_blocking() */
+
+/* ---- readback -------------------------------------------------------------------------- */
+/* Raw accumulator, float[4] per pixel (sum rgb, w = sample count). Implies rpt_sync. */
+int rpt_read_output(rpt_context* ctx, float* rgba, size_t npixels);
+/* Packed RGB `output.xyz / samples` normalised on the device (src/trace.rs:199-204). */
+int rpt_read_framebuffer(rpt_context* ctx, float* rgb, size_t npixels, float samples);
+/* Diagnostics: bounce-0 triangle_index per pixel (0xFFFFFFFF = miss) for the NEXT sample index
+ * of the current rng state, without advancing any state. */
+int rpt_read_primary_ids(rpt_context* ctx, uint32_t* triangle_ids, size_t npixels);
+int rpt_get_counters(rpt_context* ctx, RptCounters* out);
+int rpt_reset_counters(rpt_context* ctx);
+/* Milliseconds the device spent in the kernels of all rpt_enqueue calls since the last
+ * rpt_reset_counters (CUDA events on the context's stream). */
+int rpt_get_device_ms(rpt_context* ctx, float* ms);
+
+/* ---- multi-GPU combine over NCCL (one rank per GPU) ------------------------------------- */
+/* id_bytes: 128-byte ncclUniqueId made by rank 0 and distributed by the host (any channel). */
+int rpt_comm_unique_id(uint8_t* id_bytes_128);
+int rpt_comm_init(rpt_context* ctx, const uint8_t* id_bytes_128, int rank, int nranks);
+/* Sum the per-rank accumulators into root's (ncclReduce over NVLink); other ranks unchanged. */
+int rpt_comm_reduce_output(rpt_context* ctx, int root);
+int rpt_comm_destroy(rpt_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPT_B200_H */

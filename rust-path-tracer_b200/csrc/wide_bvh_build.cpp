@@ -1,0 +1,274 @@
+// wide_bvh_build.cpp — collapse the reference's binary BVH (src/bvh.rs output, BVHNode[] +
+// permuted index buffer) into the backend's 8-wide compressed layout described in wide_bvh.h.
+//
+// The binary tree is treated as given: the wide tree holds exactly the same triangles under
+// conservative (never smaller) boxes, so a nearest-hit query returns the same triangle as the
+// reference traversal except for exact-t ties, which depend on visiting order.
+#include "wide_bvh.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <deque>
+
+namespace rpt {
+namespace {
+
+struct Box3 {
+    float lo[3] = {INFINITY, INFINITY, INFINITY};
+    float hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    void grow(const float* p) {
+        for (int k = 0; k < 3; ++k) { lo[k] = std::fmin(lo[k], p[k]); hi[k] = std::fmax(hi[k], p[k]); }
+    }
+    void grow(const Box3& b) {
+        for (int k = 0; k < 3; ++k) { lo[k] = std::fmin(lo[k], b.lo[k]); hi[k] = std::fmax(hi[k], b.hi[k]); }
+    }
+    double half_area() const {
+        const double e[3] = {(double)hi[0] - lo[0], (double)hi[1] - lo[1], (double)hi[2] - lo[2]};
+        return e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
+    }
+};
+
+// A subtree of the binary BVH, or a run of triangles of an over-full binary leaf.
+struct Item {
+    Box3 box;
+    bool is_range;           // true: triangles [first, first+count); false: binary node `first`
+    uint32_t first, count;
+};
+
+class Collapser {
+  public:
+    Collapser(const RptBVHNode* nodes, uint32_t nnodes, const uint32_t* tris, uint32_t ntris, const RptPerVertexData* verts,
+              uint32_t nverts, WideBvh& out)
+        : nodes_(nodes), nnodes_(nnodes), tris_(tris), ntris_(ntris), verts_(verts), nverts_(nverts), out_(out) {}
+
+    bool run(const char** error) {
+        out_.nodes.clear();
+        out_.tri_pos.clear();
+        out_.orig_index.clear();
+        out_.wide_index.assign(ntris_, 0xFFFFFFFFu);
+        out_.tri_pos.reserve((size_t)ntris_ * 12);
+        out_.orig_index.reserve(ntris_);
+
+        Item root;
+        if (!node_item(0, root)) { *error = "malformed BVH: bad root node"; return false; }
+        struct Work { uint32_t wide; Item item; uint32_t depth; };
+        std::deque<Work> queue;
+        out_.nodes.emplace_back();
+        queue.push_back({0u, root, 0u});
+        size_t visited_budget = (size_t)nnodes_ * 2 + (size_t)ntris_ * 2 + 16;
+        while (!queue.empty()) {
+            Work w = queue.front();
+            queue.pop_front();
+            out_.max_depth = std::max(out_.max_depth, w.depth);
+
+            // ---- gather up to 8 children by repeatedly opening the largest splittable one
+            std::vector<Item> kids;
+            if (splittable(w.item)) {
+                Item a, b;
+                if (!split(w.item, a, b)) { *error = "malformed BVH: child index or triangle range out of bounds"; return false; }
+                kids = {a, b};
+            } else {
+                kids = {w.item};
+            }
+            while (kids.size() < 8) {
+                int best = -1;
+                double best_area = -1.0;
+                for (size_t i = 0; i < kids.size(); ++i)
+                    if (splittable(kids[i]) && kids[i].box.half_area() > best_area) { best = (int)i; best_area = kids[i].box.half_area(); }
+                if (best < 0) break;
+                Item a, b;
+                if (!split(kids[best], a, b)) { *error = "malformed BVH: child index or triangle range out of bounds"; return false; }
+                kids[best] = a;
+                kids.push_back(b);
+                if (visited_budget-- == 0) { *error = "malformed BVH: cycle"; return false; }
+            }
+
+            // ---- octant-ordered slots: slot s prefers the child lying farthest against direction ds(s)
+            Box3 nb;
+            for (const Item& k : kids) nb.grow(k.box);
+            int slot_of[8], kid_in_slot[8];
+            assign_slots(kids, nb, slot_of, kid_in_slot);
+
+            // ---- allocate children: inner nodes contiguous in slot order, triangles in one block
+            const uint32_t child_base = (uint32_t)out_.nodes.size();
+            const uint32_t tri_base = (uint32_t)out_.orig_index.size();
+            uint32_t imask = 0, meta[8] = {0}, tri_off = 0;
+            for (int s = 0; s < 8; ++s) {
+                const int k = kid_in_slot[s];
+                if (k < 0) continue;
+                const Item& it = kids[k];
+                if (splittable(it)) {
+                    imask |= 1u << s;
+                    meta[s] = (1u << 5) | (24u + (uint32_t)s);
+                    out_.nodes.emplace_back();
+                    queue.push_back({(uint32_t)out_.nodes.size() - 1u, it, w.depth + 1u});
+                    out_.inner_children++;
+                } else {
+                    const uint32_t unary = it.count == 1 ? 1u : (it.count == 2 ? 3u : 7u);
+                    meta[s] = (unary << 5) | tri_off;
+                    for (uint32_t t = 0; t < it.count; ++t) emit_triangle(it.first + t);
+                    tri_off += it.count;
+                    out_.leaf_children++;
+                }
+            }
+            if (tri_off > 24) { *error = "internal: more than 24 triangles under one wide node"; return false; }
+            encode(out_.nodes[w.wide], nb, kids, kid_in_slot, child_base, tri_base, imask, meta);
+        }
+        for (uint32_t t = 0; t < ntris_; ++t)
+            if (out_.wide_index[t] == 0xFFFFFFFFu) { *error = "malformed BVH: a triangle is not referenced by any leaf"; return false; }
+        return true;
+    }
+
+  private:
+    bool node_item(uint32_t ni, Item& it) const {
+        if (ni >= nnodes_) return false;
+        const RptBVHNode& n = nodes_[ni];
+        std::memcpy(it.box.lo, n.aabb_min, 12);
+        std::memcpy(it.box.hi, n.aabb_max, 12);
+        if (n.triangle_count > 0) {
+            if ((uint64_t)n.left_or_first + n.triangle_count > ntris_) return false;
+            it.is_range = true;
+            it.first = n.left_or_first;
+            it.count = n.triangle_count;
+        } else {
+            if ((uint64_t)n.left_or_first + 1 >= nnodes_) return false;
+            it.is_range = false;
+            it.first = ni;
+            it.count = 0;
+        }
+        return true;
+    }
+    static bool splittable(const Item& it) { return !it.is_range || it.count > 3; }
+    Box3 range_box(uint32_t first, uint32_t count) const {
+        Box3 b;
+        for (uint32_t t = first; t < first + count; ++t)
+            for (int k = 0; k < 3; ++k) b.grow(verts_[tris_[4 * (size_t)t + k]].vertex);
+        return b;
+    }
+    bool split(const Item& it, Item& a, Item& b) const {
+        if (!it.is_range) {
+            const uint32_t l = nodes_[it.first].left_or_first;
+            return node_item(l, a) && node_item(l + 1, b);
+        }
+        const uint32_t half = it.count / 2;
+        a = {range_box(it.first, half), true, it.first, half};
+        b = {range_box(it.first + half, it.count - half), true, it.first + half, it.count - half};
+        return true;
+    }
+
+    static void assign_slots(const std::vector<Item>& kids, const Box3& nb, int* slot_of, int* kid_in_slot) {
+        const int n = (int)kids.size();
+        double cost[8][8];
+        const double nc[3] = {0.5 * ((double)nb.lo[0] + nb.hi[0]), 0.5 * ((double)nb.lo[1] + nb.hi[1]), 0.5 * ((double)nb.lo[2] + nb.hi[2])};
+        for (int s = 0; s < 8; ++s) {
+            const double ds[3] = {(s & 4) ? -1.0 : 1.0, (s & 2) ? -1.0 : 1.0, (s & 1) ? -1.0 : 1.0};
+            for (int i = 0; i < n; ++i) {
+                double c = 0.0;
+                for (int k = 0; k < 3; ++k) c += (0.5 * ((double)kids[i].box.lo[k] + kids[i].box.hi[k]) - nc[k]) * ds[k];
+                cost[s][i] = c;
+            }
+        }
+        for (int s = 0; s < 8; ++s) kid_in_slot[s] = -1;
+        for (int i = 0; i < 8; ++i) slot_of[i] = -1;
+        for (int round = 0; round < n; ++round) {  // greedy: cheapest remaining (slot, child) pair
+            double best = DBL_MAX;
+            int bs = -1, bi = -1;
+            for (int s = 0; s < 8; ++s) {
+                if (kid_in_slot[s] >= 0) continue;
+                for (int i = 0; i < n; ++i)
+                    if (slot_of[i] < 0 && cost[s][i] < best) { best = cost[s][i]; bs = s; bi = i; }
+            }
+            kid_in_slot[bs] = bi;
+            slot_of[bi] = bs;
+        }
+    }
+
+    void emit_triangle(uint32_t t) {
+        const uint32_t* tri = tris_ + 4 * (size_t)t;
+        const float* a = verts_[tri[0]].vertex;
+        const float* b = verts_[tri[1]].vertex;
+        const float* c = verts_[tri[2]].vertex;
+        float rec[12];
+        uint32_t bits;
+        rec[0] = a[0]; rec[1] = a[1]; rec[2] = a[2];
+        bits = t; std::memcpy(&rec[3], &bits, 4);
+        rec[4] = b[0] - a[0]; rec[5] = b[1] - a[1]; rec[6] = b[2] - a[2];
+        bits = tri[3]; std::memcpy(&rec[7], &bits, 4);
+        rec[8] = c[0] - a[0]; rec[9] = c[1] - a[1]; rec[10] = c[2] - a[2];
+        rec[11] = 0.0f;
+        out_.wide_index[t] = (uint32_t)out_.orig_index.size();
+        out_.orig_index.push_back(t);
+        out_.tri_pos.insert(out_.tri_pos.end(), rec, rec + 12);
+    }
+
+    static void encode(WideNode& node, const Box3& nb, const std::vector<Item>& kids, const int* kid_in_slot, uint32_t child_base,
+                       uint32_t tri_base, uint32_t imask, const uint32_t* meta) {
+        uint8_t e[3];
+        double cell[3];
+        for (int k = 0; k < 3; ++k) {
+            const double extent = (double)nb.hi[k] - (double)nb.lo[k];
+            int ex = -126;
+            if (extent > 0.0) {
+                ex = (int)std::ceil(std::log2(extent / 255.0));
+                while (std::ceil(extent / std::ldexp(1.0, ex)) > 255.0) ++ex;  // log2 rounding guard
+            }
+            ex = std::min(std::max(ex, -126), 127);
+            e[k] = (uint8_t)(ex + 127);
+            cell[k] = std::ldexp(1.0, ex);
+        }
+        uint8_t q[6][8];
+        std::memset(q, 0, sizeof(q));
+        for (int s = 0; s < 8; ++s) {
+            const int ki = kid_in_slot[s];
+            if (ki < 0) continue;
+            const Box3& b = kids[ki].box;
+            for (int k = 0; k < 3; ++k) {
+                const double lo = std::floor(((double)b.lo[k] - (double)nb.lo[k]) / cell[k]);
+                const double hi = std::ceil(((double)b.hi[k] - (double)nb.lo[k]) / cell[k]);
+                q[k][s] = (uint8_t)std::min(std::max(lo, 0.0), 255.0);
+                q[3 + k][s] = (uint8_t)std::min(std::max(hi, 0.0), 255.0);
+            }
+        }
+        auto pack4 = [](const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
+        uint8_t m8[8];
+        for (int s = 0; s < 8; ++s) m8[s] = (uint8_t)meta[s];
+        uint32_t* w = node.w;
+        std::memcpy(&w[0], &nb.lo[0], 4);
+        std::memcpy(&w[1], &nb.lo[1], 4);
+        std::memcpy(&w[2], &nb.lo[2], 4);
+        w[3] = (uint32_t)e[0] | ((uint32_t)e[1] << 8) | ((uint32_t)e[2] << 16) | (imask << 24);
+        w[4] = child_base; w[5] = tri_base; w[6] = pack4(m8); w[7] = pack4(m8 + 4);
+        w[8] = pack4(q[0]); w[9] = pack4(q[0] + 4); w[10] = pack4(q[1]); w[11] = pack4(q[1] + 4);
+        w[12] = pack4(q[2]); w[13] = pack4(q[2] + 4); w[14] = pack4(q[3]); w[15] = pack4(q[3] + 4);
+        w[16] = pack4(q[4]); w[17] = pack4(q[4] + 4); w[18] = pack4(q[5]); w[19] = pack4(q[5] + 4);
+    }
+
+    const RptBVHNode* nodes_;
+    uint32_t nnodes_;
+    const uint32_t* tris_;
+    uint32_t ntris_;
+    const RptPerVertexData* verts_;
+    uint32_t nverts_;
+    WideBvh& out_;
+};
+
+}  // namespace
+
+bool build_wide_bvh(const RptBVHNode* nodes, uint32_t nnodes, const uint32_t* triangles, uint32_t ntriangles,
+                    const RptPerVertexData* vertices, uint32_t nvertices, WideBvh& out, const char** error) {
+    static const char* none = "";
+    const char* dummy = none;
+    if (!error) error = &dummy;
+    *error = none;
+    if (!nodes || !triangles || !vertices || nnodes == 0 || ntriangles == 0) { *error = "empty scene"; return false; }
+    for (size_t t = 0; t < (size_t)ntriangles; ++t)
+        for (int k = 0; k < 3; ++k)
+            if (triangles[4 * t + k] >= nvertices) { *error = "triangle references a vertex out of range"; return false; }
+    out = WideBvh{};
+    Collapser c(nodes, nnodes, triangles, ntriangles, vertices, nvertices, out);
+    return c.run(error);
+}
+
+}  // namespace rpt

@@ -1,0 +1,57 @@
+// wide_harness.cpp — TEST-ONLY host build of the backend's wide-BVH code.
+//
+// The 8-wide BVH collapse (csrc/wide_bvh_build.cpp) and its traversal (csrc/dev/wide_bvh.cuh)
+// are plain C++ apart from a handful of intrinsics, so this harness compiles them with g++
+// (-ffp-contract=off) to check, without a GPU, that the re-laid-out tree returns the same
+// triangle and the same t bits as the reference traversal restated in oracle/oracle.cpp.
+// It is not part of the product: nothing under rust-path-tracer_b200/ builds or loads it.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../rust-path-tracer_b200/csrc/dev/wide_bvh.cuh"
+#include "../../rust-path-tracer_b200/csrc/wide_bvh.h"
+
+namespace {
+struct LocalStack {
+    rpt::uint2 data[rpt::kWideStackCapacity];
+    int n = 0;
+    int high_water = 0;
+    void push(rpt::uint2 v) { data[n++] = v; if (n > high_water) high_water = n; }
+    rpt::uint2 pop() { return data[--n]; }
+    bool empty() const { return n == 0; }
+};
+}  // namespace
+
+extern "C" {
+
+// out_stats: [0] nodes, [1] max_depth, [2] inner_children, [3] leaf_children, [4] stack high-water
+int harness_wide_intersect(const RptPerVertexData* verts, uint32_t nverts, const uint32_t* tris, uint32_t ntris, const RptBVHNode* nodes,
+                           uint32_t nnodes, const float* rays_o_d, uint32_t nrays, int any_hit, const float* max_t, uint32_t* out_hit,
+                           uint32_t* out_tri, float* out_t, uint32_t* out_backface, uint32_t* out_stats) {
+    rpt::WideBvh wide;
+    const char* err = "";
+    if (!rpt::build_wide_bvh(nodes, nnodes, tris, ntris, verts, nverts, wide, &err)) return -1;
+    rpt::WideScene scene{reinterpret_cast<const rpt::uint4*>(wide.nodes.data()), reinterpret_cast<const rpt::float4*>(wide.tri_pos.data())};
+    int high = 0;
+    for (uint32_t i = 0; i < nrays; ++i) {
+        const float* r = rays_o_d + 6 * (size_t)i;
+        LocalStack st;
+        rpt::WideHit h = any_hit ? rpt::wide_intersect<false>(scene, rpt::mk3(r[0], r[1], r[2]), rpt::mk3(r[3], r[4], r[5]), max_t[i], st)
+                                 : rpt::wide_intersect<true>(scene, rpt::mk3(r[0], r[1], r[2]), rpt::mk3(r[3], r[4], r[5]), 0.0f, st);
+        out_hit[i] = h.hit;
+        out_tri[i] = h.hit ? wide.orig_index[h.triangle] : 0u;
+        out_t[i] = h.t;
+        out_backface[i] = h.backface;
+        if (st.high_water > high) high = st.high_water;
+    }
+    if (out_stats) {
+        out_stats[0] = (uint32_t)wide.nodes.size();
+        out_stats[1] = wide.max_depth;
+        out_stats[2] = wide.inner_children;
+        out_stats[3] = wide.leaf_children;
+        out_stats[4] = (uint32_t)high;
+    }
+    return 0;
+}
+}
