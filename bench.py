@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mpaths/s (and Mrays/s) of the tracing hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+A *step* is one pass of the hot path over one batch: `spp_per_step` sample indices for every
+pixel of the frame (one `rpt_enqueue`).  Workloads (BASELINE.json `configs`; scenes come from the
+committed fixtures under tests/golden/scenes, sample indices from the blue-noise seed table):
+
+    cornell   (default) configs[1]: DarkCornell 1024x1024, NEE with MIS; K=16 steps x 64 spp = its 1024 spp
+    furnace   configs[0]: FurnaceTest 256x256, 64 spp (4 steps x 16)
+    pbr       configs[2]: PBRTest 1920x1080, procedural sky
+    veach     configs[3]: VeachMIS 1920x1080, MIS
+
+N > 1 (torchrun, one rank per GPU): every rank renders the full frame over its own sample-index
+range (rank r starts at sample r * K * spp) — per-GPU work is fixed, so scaling is "weak" — and the
+per-GPU accumulators are combined once, inside the timed region, by ncclReduce over NVLink.
+
+Keys beyond the base contract: `mrays_per_s`, `roofline` (extend kernel), `cpu_baseline`
+(oracle on the host cores), `e2e` (same metric through the C ABI with host buffers in the timed
+region), `clocks`, `gpu_launches`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (scene, width, height, nee, spp_per_step, config name)
+    "cornell": ("DarkCornell", 1024, 1024, 1, 64, "configs[1] DarkCornell.glb 1024x1024, NEE (MIS)"),
+    "furnace": ("FurnaceTest", 256, 256, 0, 16, "configs[0] FurnaceTest.glb 256x256"),
+    "pbr": ("PBRTest", 1920, 1080, 0, 16, "configs[2] PBRTest.glb 1920x1080, procedural sky"),
+    "veach": ("VeachMIS", 1920, 1080, 1, 32, "configs[3] VeachMIS.glb 1920x1080, MIS"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_workload(name):
+    from rust_path_tracer_b200.capi import TracingConfig
+    from rust_path_tracer_b200.world import World, make_rng_seeds
+
+    scene, w, h, nee, spp, label = WORKLOADS[name]
+    world = World.from_path(os.path.join(REPO, "tests", "golden", "scenes", scene + ".npz"))
+    if world is None:
+        raise SystemExit(f"cannot load scene fixture for {scene}")
+    cfg = TracingConfig.default(w, h)
+    cfg.nee = nee
+    return world, cfg, make_rng_seeds(w, h), spp, label, scene
+
+
+def oracle_sample(world, cfg, seeds, spp, threads=0):
+    """Time the CPU oracle on `spp` samples of the workload; returns (seconds, counters)."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import oracle as oracle_mod
+
+    scene = oracle_mod.OracleScene(world)
+    t0 = time.perf_counter()
+    _, _, ctr, _ = oracle_mod.trace(cfg, scene, seeds, spp, threads=threads)
+    return time.perf_counter() - t0, ctr, oracle_mod.max_threads() if threads == 0 else threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The Rust crate cannot be
+    built in this image (no Rust toolchain), so this arm times the oracle port — the C++ restatement
+    of trace_cpu + kernels::trace_pixel — with all host threads; each step is a bounded sample
+    (1 spp of the frame) of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world, cfg, seeds, _spp, label, scene = load_workload(args.workload)
+    ref_spp = 1
+    for _ in range(args.warmup):
+        oracle_sample(world, cfg, seeds, ref_spp)
+    times, rays = [], 0
+    for _ in range(args.steps):
+        dt, ctr, threads = oracle_sample(world, cfg, seeds, ref_spp)
+        times.append(dt)
+        rays += ctr["nearest_rays"] + ctr["any_rays"]
+    total = sum(times)
+    paths = cfg.width * cfg.height * ref_spp * args.steps
+    value = paths / total / 1e6
+    line = {
+        "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": label, "scene": scene + " (fixture of the shipped .glb)", "width": cfg.width, "height": cfg.height,
+                   "nee": cfg.nee, "spp_per_step": ref_spp},
+        "mrays_per_s": rays / total / 1e6,
+        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": threads, "kind": "port",
+                         "sample": f"{ref_spp} spp of the full {cfg.width}x{cfg.height} frame per step, OpenMP rows"},
+        "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+
+    from rust_path_tracer_b200 import capi
+    from rust_path_tracer_b200.trace import Renderer
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the tracing backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    world, cfg, seeds0, spp, label, scene = load_workload(args.workload)
+    if args.spp:
+        spp = args.spp
+    npix = cfg.width * cfg.height
+    pipeline = capi.PIPELINE_MEGAKERNEL if args.pipeline == "megakernel" else capi.PIPELINE_WAVEFRONT
+    r = Renderer(local_rank, pipeline)
+    r.upload_world(world)
+    r.set_config(cfg)
+    if args.wave_slots:
+        r.set_wave_slots(args.wave_slots)
+    # sample-index-range split: rank r owns samples [r*K*spp, (r+1)*K*spp) (+ warm-up samples first)
+    seeds = seeds0.copy()
+    seeds[:, 0] += np.uint32(rank * (args.steps + args.warmup) * spp)
+    r.write_rng(seeds)
+    if dist is not None:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Renderer.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        r.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world_size)
+
+    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps --------------
+    for _ in range(args.warmup):
+        r.enqueue(spp)
+    r.sync()
+    r.write_output(None)
+    r.reset_counters()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r.enqueue(spp)
+    if dist is not None:
+        r.comm_reduce_output(0)
+    r.sync()
+    barrier()
+    wall_s = time.perf_counter() - t0
+    device_ms = r.device_ms()
+    clocks = sampler.stop() if sampler else None
+    ctr = r.counters()
+    # the job's time is the slowest rank's; device time (CUDA events on the launching stream) where available
+    times = torch.tensor([wall_s, device_ms / 1e3], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([ctr["paths"], ctr["nearest_rays"] + ctr["any_rays"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    wall_s, dev_s = float(times[0]), float(times[1])
+    job_s = wall_s if dist is not None else max(dev_s, 1e-9)  # multi-GPU: include the reduce (outside the per-enqueue events)
+    total_paths, total_rays = float(counts[0]), float(counts[1])
+    value = total_paths / job_s / 1e6
+
+    line = {
+        "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * job_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": label, "scene": scene + " (fixture of the shipped .glb)", "width": cfg.width, "height": cfg.height,
+                   "nee": cfg.nee, "min_bounces": cfg.min_bounces, "max_bounces": cfg.max_bounces, "spp_per_step": spp,
+                   "pipeline": args.pipeline, "partition": f"sample-index range x{world_size} + ncclReduce" if world_size > 1 else "single GPU",
+                   "l2": "working set per step (path state %.0f MB) exceeds the 126 MB L2" % (152.0 * min(npix * spp, args.wave_slots or (1 << 21)) / 1e6)},
+        "mrays_per_s": total_rays / job_s / 1e6,
+        "wall_ms_per_step": 1e3 * wall_s / args.steps,
+        "gpu_launches": ctr["kernel_launches"],
+        "clocks": clocks,
+    }
+
+    if rank == 0 and not args.quick:
+        # ---- roofline of the dominant kernel (extend): per-launch durations from CUDA events --
+        r.set_stage_timing(True)
+        r.reset_counters()
+        r.enqueue(spp)
+        stages = r.stage_timing()
+        c1 = r.counters()
+        r.set_stage_timing(False)
+        ext_ms, ext_launches = stages["extend"] if pipeline == capi.PIPELINE_WAVEFRONT else stages["megakernel"]
+        # algorithmic bytes per nearest ray, in the reference's layout: 32 B per box slab-tested + 64 B per
+        # triangle tested (16 B index + 3 x 16 B positions) — SURVEY.md §8(d); counted by the oracle on 1 spp
+        dt1, octr, threads = oracle_sample(world, cfg, seeds0, 1)
+        boxes_n = octr["boxes_tested"] - octr["boxes_tested_any"]
+        tris_n = octr["tris_tested"] - octr["tris_tested_any"]
+        bytes_per_ray = (32.0 * boxes_n + 64.0 * tris_n) / max(octr["nearest_rays"], 1)
+        peak, peak_src = measured_peaks()
+        rays_per_launch = c1["nearest_rays"] / max(ext_launches, 1)
+        ms_per_launch = ext_ms / max(ext_launches, 1)
+        achieved = rays_per_launch * bytes_per_ray / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else 0.0
+        if pipeline != capi.PIPELINE_WAVEFRONT:  # the megakernel traces shadow rays in the same launch
+            bytes_any = (32.0 * octr["boxes_tested_any"] + 64.0 * octr["tris_tested_any"]) / max(octr["any_rays"], 1)
+            achieved = (c1["nearest_rays"] * bytes_per_ray + c1["any_rays"] * bytes_any) / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        line["roofline"] = {
+            "bound": "hbm", "kernel": "wf_extend_kernel" if pipeline == capi.PIPELINE_WAVEFRONT else "mega_trace_kernel",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch,
+            "ms_per_launch": ms_per_launch, "launches_timed": ext_launches,
+            "stage_ms": {k: v[0] for k, v in stages.items() if v[1]},
+            "note": "scene is L2-resident: algorithmic bytes are served by L1/L2, so frac can exceed DRAM traffic; see DESIGN.md",
+        }
+        # ---- CPU baseline: the oracle port on the host cores, bounded sample ------------------
+        cpu_spp = max(1, min(8, int(15.0 / max(dt1, 1e-3))))
+        dtc, cctr, threads = oracle_sample(world, cfg, seeds0, cpu_spp)
+        line["cpu_baseline"] = {"value": npix * cpu_spp / dtc / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "port",
+                                "mrays_per_s": (cctr["nearest_rays"] + cctr["any_rays"]) / dtc / 1e6,
+                                "sample": f"{cpu_spp} spp of the full {cfg.width}x{cfg.height} frame ({dtc:.1f} s), OpenMP rows"}
+
+    # ---- end to end through the C ABI with host buffers: H2D seeds + config, enqueue, D2H frame --
+    fb = np.empty(npix * 3, np.float32)
+    step_seeds = seeds.copy()
+    r.write_output(None)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_seeds[:, 0] = seeds[:, 0] + np.uint32(k * spp)
+        r.set_config(cfg)
+        r.write_rng(step_seeds)
+        r.enqueue(spp)
+        r.read_framebuffer(float((k + 1) * spp), fb)
+    barrier()
+    e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    line["e2e"] = {"value": npix * spp * args.steps * world_size / float(e2e[0]) / 1e6, "unit": "Mpaths/s",
+                   "h2d_bytes_per_step": 80 + 8 * npix, "d2h_bytes_per_step": 12 * npix,
+                   "what": "per step: rpt_set_config + rpt_write_rng (host seeds) + rpt_enqueue + rpt_read_framebuffer (host RGB)"}
+    if not np.isfinite(fb).all():
+        line["e2e"]["nan_pixels"] = int((~np.isfinite(fb.reshape(-1, 3)).all(axis=1)).sum())
+
+    if dist is not None:
+        r.comm_destroy()
+    r.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cornell")
+    ap.add_argument("--pipeline", choices=["wavefront", "megakernel"], default="wavefront")
+    ap.add_argument("--spp", type=int, default=0, help="samples per step (default: the workload's)")
+    ap.add_argument("--wave-slots", type=int, default=0)
+    ap.add_argument("--quick", action="store_true", help="skip the roofline and cpu_baseline legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 16:
+            args.steps = 4
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,6 +105,18 @@ int rpt_reset_counters(rpt_context* ctx);
  * rpt_reset_counters (CUDA events on the context's stream). */
 int rpt_get_device_ms(rpt_context* ctx, float* ms);
 
+/* Per-stage device time, for roofline accounting.  While enabled, every kernel launch of
+ * rpt_enqueue is bracketed by CUDA events on the context's stream (this perturbs the pipeline a
+ * little, so whole-job throughput is measured with it off). */
+enum { RPT_STAGE_GENERATE = 0, RPT_STAGE_EXTEND, RPT_STAGE_MISS, RPT_STAGE_SHADE, RPT_STAGE_SHADOW, RPT_STAGE_ACCUMULATE,
+       RPT_STAGE_MEGAKERNEL, RPT_STAGE_OTHER, RPT_STAGE_COUNT };
+typedef struct RptStageTiming {
+    float ms[RPT_STAGE_COUNT];          /* summed launch durations */
+    uint64_t launches[RPT_STAGE_COUNT]; /* launches timed */
+} RptStageTiming;
+int rpt_set_stage_timing(rpt_context* ctx, int enable);
+int rpt_get_stage_timing(rpt_context* ctx, RptStageTiming* out); /* syncs; clears the totals */
+
 /* ---- multi-GPU combine over NCCL (one rank per GPU) ------------------------------------- */
 /* id_bytes: 128-byte ncclUniqueId made by rank 0 and distributed by the host (any channel). */
 int rpt_comm_unique_id(uint8_t* id_bytes_128);

@@ -112,10 +112,12 @@ struct Image {
 
 struct Counters {
     uint64_t nearest_rays = 0, any_rays = 0, nodes_popped = 0, boxes_tested = 0, tris_tested = 0;
+    uint64_t boxes_tested_any = 0, tris_tested_any = 0;  // the share of the two totals spent in intersect_any
     uint64_t stack_overflows = 0, light_index_clamped = 0;
     void add(const Counters& o) {
         nearest_rays += o.nearest_rays; any_rays += o.any_rays; nodes_popped += o.nodes_popped;
         boxes_tested += o.boxes_tested; tris_tested += o.tris_tested;
+        boxes_tested_any += o.boxes_tested_any; tris_tested_any += o.tris_tested_any;
         stack_overflows += o.stack_overflows; light_index_clamped += o.light_index_clamped;
     }
 };
@@ -218,6 +220,7 @@ TraceResult intersect_front_to_back(const Scene& s, V3 ro, V3 rd, float max_t, C
                 float t = 0.0f;
                 bool backface = false;
                 ctr.tris_tested++;
+                if (!NEAREST) ctr.tris_tested_any++;
                 if (muller_trumbore(ro, rd, a, b, c, t, backface) && t > 0.001f && t < result.t && (NEAREST || t <= max_t)) {
                     std::memcpy(result.tri, tri, 16);
                     result.triangle_index = ti;
@@ -232,6 +235,7 @@ TraceResult intersect_front_to_back(const Scene& s, V3 ro, V3 rd, float max_t, C
             float near_d = intersect_aabb(s.nodes[near_i], ro, rd, result.t);
             float far_d = intersect_aabb(s.nodes[far_i], ro, rd, result.t);
             ctr.boxes_tested += 2;
+            if (!NEAREST) ctr.boxes_tested_any += 2;
             if (near_d > far_d) {
                 std::swap(near_i, far_i);
                 std::swap(near_d, far_d);
@@ -698,6 +702,7 @@ struct OracleWorld {
 struct OracleCounters {
     uint64_t paths, nearest_rays, any_rays, nodes_popped, boxes_tested, tris_tested;
     uint64_t stack_overflows, light_index_clamped, rng_exhausted;
+    uint64_t boxes_tested_any, tris_tested_any;
 };
 
 int oracle_max_threads() {
@@ -763,6 +768,8 @@ int oracle_trace(const RptTracingConfig* cfg, const OracleWorld* w, uint32_t* rn
         counters_out->stack_overflows = total.stack_overflows;
         counters_out->light_index_clamped = total.light_index_clamped;
         counters_out->rng_exhausted = exhausted;
+        counters_out->boxes_tested_any = total.boxes_tested_any;
+        counters_out->tris_tested_any = total.tris_tested_any;
     }
     return 0;
 }

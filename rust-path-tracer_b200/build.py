@@ -66,7 +66,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OUT_DIR, os.path.basename(src) + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc, *ARCH_FLAGS, *NVCC_FLAGS, "-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-x", "cu", "-c", src, "-o", obj]
+            extra = ["-fmad=false"] if src.endswith("_nofma.cu") else []
+            cmd = [nvcc, *ARCH_FLAGS, *NVCC_FLAGS, *extra, "-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-x", "cu", "-c", src, "-o", obj]
             jobs.append((src, cmd))
 
     def run(job):

@@ -24,7 +24,7 @@ DEVICE_SYMBOLS = [
     "rpt_create", "rpt_destroy", "rpt_last_error", "rpt_set_pipeline", "rpt_set_wave_slots", "rpt_upload_world",
     "rpt_set_config", "rpt_write_rng", "rpt_read_rng", "rpt_write_output", "rpt_set_tile_partition", "rpt_enqueue",
     "rpt_sync", "rpt_read_output", "rpt_read_framebuffer", "rpt_read_primary_ids", "rpt_get_counters",
-    "rpt_reset_counters", "rpt_get_device_ms", "rpt_comm_unique_id", "rpt_comm_init", "rpt_comm_reduce_output",
+    "rpt_reset_counters", "rpt_get_device_ms", "rpt_set_stage_timing", "rpt_get_stage_timing", "rpt_comm_unique_id", "rpt_comm_init", "rpt_comm_reduce_output",
     "rpt_comm_destroy",
 ]
 
@@ -71,6 +71,13 @@ assert C.sizeof(TracingConfig) == 80
 
 class Counters(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("nearest_rays", C.c_uint64), ("any_rays", C.c_uint64), ("kernel_launches", C.c_uint64)]
+
+
+STAGES = ["generate", "extend", "miss", "shade", "shadow", "accumulate", "megakernel", "other"]
+
+
+class StageTiming(C.Structure):
+    _fields_ = [("ms", C.c_float * 8), ("launches", C.c_uint64 * 8)]
 
 
 BVH_NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("triangle_count", "<u4"), ("aabb_max", "<f4", 3), ("left_or_first", "<u4")])

@@ -1,0 +1,818 @@
+// context.cu — implementation of the C ABI in include/rpt_b200.h: one context = one B200.
+//
+// Owns every device allocation (the reference-layout scene copy used by the megakernel arm, the
+// private wide-BVH / triangle-stream / light-record layouts used by the wavefront pipeline, the
+// rng and accumulation buffers, and the path-state arrays of a wave), and drives the wavefront
+// loop: per wave  generate -> { extend -> miss | shade -> shadow-connect } x max_bounces ->
+// accumulate, all on one stream with queue lengths kept on the device (no host round-trips).
+// Every failure becomes a status code + message; nothing throws or aborts across the ABI.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rpt_b200.h"
+#include "../../include/rpt_host.h"
+#include "device_scene.h"
+#include "wide_bvh.h"
+
+using namespace rpt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const T* host, size_t count, cudaStream_t s) {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+// ---- NCCL, resolved at run time so the library loads (and host-only tests run) without it ----
+struct NcclUniqueId {  // ncclUniqueId: 128 opaque bytes, passed BY VALUE to ncclCommInitRank
+    char internal[128];
+};
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (handle) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(handle, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(handle, "ncclCommInitRank"));
+        Reduce = reinterpret_cast<decltype(Reduce)>(dlsym(handle, "ncclReduce"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+        if (!GetUniqueId || !CommInitRank || !Reduce || !CommDestroy) { err = "libnccl is missing expected symbols"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+}  // namespace
+
+struct rpt_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    int pipeline = RPT_PIPELINE_WAVEFRONT;
+    uint32_t wave_slots = 1u << 21;
+
+    // scene, reference layouts (megakernel arm)
+    DevBuf<RptPerVertexData> d_vertices;
+    DevBuf<uint4> d_triangles;
+    DevBuf<RptBVHNode> d_nodes;
+    DevBuf<RptMaterialData> d_materials;
+    DevBuf<RptLightPickEntry> d_lights;
+    DevBuf<uchar4> d_atlas;
+    DevBuf<float4> d_sky;
+    uint32_t atlas_w = 1, atlas_h = 1, sky_w = 2, sky_h = 2, nlights = 0, nmaterials = 0;
+    // scene, private layouts (wavefront arm)
+    DevBuf<uint4> d_wide_nodes;
+    DevBuf<float4> d_tri_pos, d_tri_shade, d_tri_tangent;
+    DevBuf<LightBin> d_light_bins;
+    DevBuf<LightRecord> d_light_records;
+    uint32_t nbins = 0;
+    bool has_world = false;
+    bool scene_closed_hint = false;
+
+    // render state
+    RptTracingConfig config{};
+    bool has_config = false;
+    Camera camera{};
+    float sky_yaw_sin = 0.0f, sky_yaw_cos = 1.0f;
+    DevBuf<uint2> d_rng;
+    DevBuf<float4> d_output;
+    DevBuf<float> d_rgb;
+    DevBuf<uint32_t> d_ids;
+    bool rng_written = false;
+    uint32_t tile_rank = 0, tile_count = 1;
+    DevBuf<uint32_t> d_pixel_map;
+    uint32_t pixel_map_len = 0;
+
+    // wave state
+    uint32_t wave_capacity = 0;
+    DevBuf<float4> w_ray_o, w_ray_d, w_thr, w_rad, w_mis_a, w_mis_b, w_sh_o, w_sh_d, w_sh_c;
+    DevBuf<uint2> w_hit;
+    DevBuf<uint32_t> w_q0, w_q1, w_qhit, w_qmiss;
+    DevBuf<WaveCtl> w_ctl;
+    DevBuf<unsigned long long> d_counters;
+
+    uint64_t kernel_launches = 0;
+    uint64_t mega_paths = 0;
+    bool stage_timing = false;
+    struct StageEvent { int stage; cudaEvent_t e0, e1; };
+    std::vector<StageEvent> stage_events;
+    RptStageTiming stage_totals{};
+
+    // Run `launch` as one counted kernel launch of `stage`, bracketed by events when stage timing is on.
+    template <class Fn>
+    void launch(int stage, Fn&& fn) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        const bool timed_launch = stage_timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+        if (timed_launch) cudaEventRecord(e0, stream);
+        fn();
+        if (timed_launch) { cudaEventRecord(e1, stream); stage_events.push_back({stage, e0, e1}); }
+        kernel_launches++;
+    }
+    void drain_stage_events() {
+        for (auto& ev : stage_events) {
+            float t = 0.0f;
+            if (cudaEventElapsedTime(&t, ev.e0, ev.e1) == cudaSuccess) { stage_totals.ms[ev.stage] += t; stage_totals.launches[ev.stage]++; }
+            cudaEventDestroy(ev.e0);
+            cudaEventDestroy(ev.e1);
+        }
+        stage_events.clear();
+    }
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+    float device_ms = 0.0f;
+
+    void* nccl_comm = nullptr;
+    int nccl_rank = 0, nccl_nranks = 1;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        error = buf;
+        return code;
+    }
+    int cuda(cudaError_t e, const char* what) {
+        if (e == cudaSuccess) return RPT_OK;
+        return fail(RPT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    uint32_t npixels() const { return config.width * config.height; }
+};
+
+#define RPT_TRY(expr)                        \
+    do {                                     \
+        const int rpt_status_ = (expr);      \
+        if (rpt_status_ != RPT_OK) return rpt_status_; \
+    } while (0)
+#define RPT_CUDA(ctx, expr) RPT_TRY((ctx)->cuda((expr), #expr))
+
+namespace {
+
+int bind_device(rpt_context* c) { return c->cuda(cudaSetDevice(c->device), "cudaSetDevice"); }
+
+FrameParams frame_params(const rpt_context* c) {
+    FrameParams f{};
+    f.camera = c->camera;
+    f.width = c->config.width;
+    f.height = c->config.height;
+    f.min_bounces = c->config.min_bounces;
+    f.max_bounces = c->config.max_bounces;
+    f.nee = c->config.nee <= 2 ? c->config.nee : 0;  // NextEventEstimation::from_u32
+    f.has_skybox = c->config.has_skybox;
+    f.clamp_lo = c->config.specular_weight_clamp[0];
+    f.clamp_hi = c->config.specular_weight_clamp[1];
+    f.sun_dir = mk3(c->config.sun_direction[0], c->config.sun_direction[1], c->config.sun_direction[2]);
+    f.sun_intensity = c->config.sun_direction[3];
+    f.sky = SkyImage{c->d_sky.p, c->sky_w, c->sky_h, c->sky_yaw_sin, c->sky_yaw_cos, c->config.sun_direction[3] * (1.0f / 15.0f)};
+    f.atlas = Atlas{c->d_atlas.p, c->atlas_w, c->atlas_h};
+    f.tile_rank = c->tile_rank;
+    f.tile_count = c->tile_count;
+    return f;
+}
+
+MegaParams mega_params(const rpt_context* c) {
+    const FrameParams f = frame_params(c);
+    MegaParams p{};
+    p.camera = f.camera;
+    p.width = f.width; p.height = f.height; p.min_bounces = f.min_bounces; p.max_bounces = f.max_bounces;
+    p.nee = f.nee; p.has_skybox = f.has_skybox; p.clamp_lo = f.clamp_lo; p.clamp_hi = f.clamp_hi;
+    p.sun_dir = f.sun_dir; p.sun_intensity = f.sun_intensity; p.sky = f.sky;
+    p.atlas = c->d_atlas.p; p.atlas_w = c->atlas_w; p.atlas_h = c->atlas_h;
+    p.nodes = reinterpret_cast<const float4*>(c->d_nodes.p);
+    p.triangles = c->d_triangles.p;
+    p.vertices = reinterpret_cast<const float4*>(c->d_vertices.p);
+    p.materials = c->d_materials.p;
+    p.lights = c->d_lights.p;
+    p.nlights = c->nlights;
+    p.rng = c->d_rng.p;
+    p.output = c->d_output.p;
+    p.counters = c->d_counters.p;
+    p.tile_rank = c->tile_rank;
+    p.tile_count = c->tile_count;
+    return p;
+}
+
+WideWorld wide_world(const rpt_context* c) {
+    WideWorld w{};
+    w.bvh = WideScene{c->d_wide_nodes.p, c->d_tri_pos.p};
+    w.tri_shade = c->d_tri_shade.p;
+    w.tri_tangent = c->d_tri_tangent.p;
+    w.materials = c->d_materials.p;
+    w.nmaterials = c->nmaterials;
+    w.light_bins = c->d_light_bins.p;
+    w.nbins = c->nbins;
+    w.lights = c->d_light_records.p;
+    return w;
+}
+
+WaveState wave_state(rpt_context* c) {
+    WaveState s{};
+    s.ray_o = c->w_ray_o.p; s.ray_d = c->w_ray_d.p; s.thr = c->w_thr.p; s.rad = c->w_rad.p;
+    s.mis_a = c->w_mis_a.p; s.mis_b = c->w_mis_b.p; s.hit = c->w_hit.p;
+    s.sh_o = c->w_sh_o.p; s.sh_d = c->w_sh_d.p; s.sh_c = c->w_sh_c.p;
+    s.q_ext[0] = c->w_q0.p; s.q_ext[1] = c->w_q1.p; s.q_hit = c->w_qhit.p; s.q_miss = c->w_qmiss.p;
+    s.ctl = c->w_ctl.p;
+    s.counters = c->d_counters.p;
+    return s;
+}
+
+int ensure_wave(rpt_context* c, uint32_t slots) {
+    if (slots <= c->wave_capacity) return RPT_OK;
+    RPT_CUDA(c, c->w_ray_o.alloc(slots)); RPT_CUDA(c, c->w_ray_d.alloc(slots)); RPT_CUDA(c, c->w_thr.alloc(slots));
+    RPT_CUDA(c, c->w_rad.alloc(slots)); RPT_CUDA(c, c->w_mis_a.alloc(slots)); RPT_CUDA(c, c->w_mis_b.alloc(slots));
+    RPT_CUDA(c, c->w_sh_o.alloc(slots)); RPT_CUDA(c, c->w_sh_d.alloc(slots)); RPT_CUDA(c, c->w_sh_c.alloc(slots));
+    RPT_CUDA(c, c->w_hit.alloc(slots));
+    RPT_CUDA(c, c->w_q0.alloc(slots)); RPT_CUDA(c, c->w_q1.alloc(slots)); RPT_CUDA(c, c->w_qhit.alloc(slots)); RPT_CUDA(c, c->w_qmiss.alloc(slots));
+    if (!c->w_ctl.p) RPT_CUDA(c, c->w_ctl.alloc(1));
+    c->wave_capacity = slots;
+    return RPT_OK;
+}
+
+// Worst-case R-sequence dimensions a path can consume (kernels/src/rng.rs:19-32 holds 32 primes,
+// index 0 unused): 2 for the camera, then per bounce 3 (BSDF) + 4 (NEE) + 1 (Russian roulette).
+uint32_t rng_dimension_budget(const RptTracingConfig& cfg) {
+    uint64_t dims = 2;
+    for (uint32_t b = 0; b < cfg.max_bounces && dims < 1000; ++b) dims += 3u + (cfg.nee != 0 && cfg.nee <= 2 ? 4u : 0u) + (b > cfg.min_bounces ? 1u : 0u);
+    return (uint32_t)std::min<uint64_t>(dims, 1000);
+}
+
+int rebuild_pixel_map(rpt_context* c) {
+    c->d_pixel_map.release();
+    c->pixel_map_len = 0;
+    if (c->tile_count <= 1 || !c->has_config) return RPT_OK;
+    const uint32_t W = c->config.width, H = c->config.height, tiles_x = (W + 31u) / 32u;
+    std::vector<uint32_t> map;
+    map.reserve((size_t)W * H / c->tile_count + 1024);
+    for (uint32_t ty = 0; ty * 32u < H; ++ty)
+        for (uint32_t tx = 0; tx < tiles_x; ++tx) {
+            if ((ty * tiles_x + tx) % c->tile_count != c->tile_rank) continue;
+            for (uint32_t y = ty * 32u; y < std::min(H, ty * 32u + 32u); ++y)
+                for (uint32_t x = tx * 32u; x < std::min(W, tx * 32u + 32u); ++x) map.push_back(y * W + x);
+        }
+    c->pixel_map_len = (uint32_t)map.size();
+    if (!map.empty()) {
+        RPT_CUDA(c, c->d_pixel_map.upload(map.data(), map.size(), c->stream));
+        RPT_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return RPT_OK;
+}
+
+int check_ready(rpt_context* c) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->has_world) return c->fail(RPT_ERR_NOT_READY, "no world uploaded (rpt_upload_world)");
+    if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "no config set (rpt_set_config)");
+    if (!c->rng_written) return c->fail(RPT_ERR_NOT_READY, "rng seeds not written (rpt_write_rng)");
+    return bind_device(c);
+}
+
+// One wave of the wavefront pipeline; `primary_only` stops after the first extend (diagnostics).
+int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids_out) {
+    const FrameParams f = frame_params(c);
+    const WideWorld w = wide_world(c);
+    const WaveState s = wave_state(c);
+    const WaveLaunch l{c->sm_count, c->stream};
+    const uint32_t nslots = d.npix * d.k_samples;
+    c->launch(RPT_STAGE_OTHER, [&] { launch_wf_reset(l, s, 1, true); });
+    c->launch(RPT_STAGE_GENERATE, [&] { launch_wf_generate(l, f, s, d, c->d_rng.p); });
+    const uint32_t bounces = primary_only ? 1u : f.max_bounces;
+    for (uint32_t b = 0; b < bounces; ++b) {
+        const int cur = (int)(b & 1u), nxt = cur ^ 1;
+        if (b > 0) c->launch(RPT_STAGE_OTHER, [&] { launch_wf_reset(l, s, nxt, false); });
+        c->launch(RPT_STAGE_EXTEND, [&] { launch_wf_extend(l, w.bvh, s, cur, b == 0, nslots); });
+        if (primary_only) {
+            c->launch(RPT_STAGE_OTHER, [&] { launch_wf_export_primary(l, w.bvh, s, d, ids_out); });
+            c->kernel_launches++;  // the export is two kernels
+            break;
+        }
+        c->launch(RPT_STAGE_MISS, [&] { launch_wf_miss(l, f, s); });
+        c->launch(RPT_STAGE_SHADE, [&] { launch_wf_shade(l, f, w, s, d, c->d_rng.p, b, nxt); });
+        if (f.nee != RPT_NEE_NONE && c->nbins > 0) c->launch(RPT_STAGE_SHADOW, [&] { launch_wf_shadow(l, w.bvh, s); });
+    }
+    if (!primary_only) c->launch(RPT_STAGE_ACCUMULATE, [&] { launch_wf_accumulate(l, s, d, c->d_rng.p, c->d_output.p); });
+    return c->cuda(cudaGetLastError(), "wavefront launch");
+}
+
+template <class Fn>
+int for_each_wave(rpt_context* c, uint32_t n_samples, Fn&& fn) {
+    const uint32_t total = c->tile_count > 1 ? c->pixel_map_len : c->npixels();
+    if (total == 0) return RPT_OK;
+    const uint32_t slots = std::max<uint32_t>(c->wave_slots, 1024u);
+    const uint32_t chunk = std::min(total, slots);
+    for (uint32_t base = 0; base < total; base += chunk) {
+        const uint32_t np = std::min(chunk, total - base);
+        const uint32_t kmax = std::max(1u, slots / np);
+        for (uint32_t s0 = 0; s0 < n_samples; s0 += kmax) {
+            WaveDesc d{base, np, std::min(kmax, n_samples - s0), c->tile_count > 1 ? c->d_pixel_map.p : nullptr};
+            RPT_TRY(ensure_wave(c, d.npix * d.k_samples));
+            RPT_TRY(fn(d));
+        }
+    }
+    return RPT_OK;
+}
+
+}  // namespace
+
+// ============================================================================ lifetime
+extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
+    if (!out_ctx) return RPT_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                         "); this backend has no CPU fallback";
+        cudaGetLastError();
+        return RPT_ERR_NO_DEVICE;
+    }
+    if (device_id < 0 || device_id >= count) {
+        g_create_error = "device id out of range";
+        return RPT_ERR_INVALID_ARGUMENT;
+    }
+    rpt_context* c = new (std::nothrow) rpt_context();
+    if (!c) return RPT_ERR_CUDA;
+    c->device = device_id;
+    cudaDeviceProp prop{};
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess || (e = c->d_counters.alloc(4)) != cudaSuccess ||
+        (e = cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream)) != cudaSuccess) {
+        g_create_error = std::string("device initialisation failed: ") + cudaGetErrorString(e);
+        delete c;
+        return RPT_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+        g_create_error = std::string("device '") + prop.name + "' is not sm_100-class; this library ships sm_100a code only";
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return RPT_ERR_NO_DEVICE;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    *out_ctx = c;
+    return RPT_OK;
+}
+
+extern "C" int rpt_destroy(rpt_context* c) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    for (auto& ev : c->timed) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    c->drain_stage_events();
+    for (auto* b : {&c->w_ray_o, &c->w_ray_d, &c->w_thr, &c->w_rad, &c->w_mis_a, &c->w_mis_b, &c->w_sh_o, &c->w_sh_d, &c->w_sh_c, &c->d_tri_pos,
+                    &c->d_tri_shade, &c->d_tri_tangent, &c->d_sky, &c->d_output})
+        b->release();
+    c->w_hit.release(); c->w_q0.release(); c->w_q1.release(); c->w_qhit.release(); c->w_qmiss.release(); c->w_ctl.release();
+    c->d_counters.release(); c->d_vertices.release(); c->d_triangles.release(); c->d_nodes.release(); c->d_materials.release();
+    c->d_lights.release(); c->d_atlas.release(); c->d_wide_nodes.release(); c->d_light_bins.release(); c->d_light_records.release();
+    c->d_rng.release(); c->d_rgb.release(); c->d_ids.release(); c->d_pixel_map.release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RPT_OK;
+}
+
+extern "C" const char* rpt_last_error(const rpt_context* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+
+extern "C" int rpt_set_pipeline(rpt_context* c, int pipeline) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    if (pipeline != RPT_PIPELINE_WAVEFRONT && pipeline != RPT_PIPELINE_MEGAKERNEL) return c->fail(RPT_ERR_INVALID_ARGUMENT, "unknown pipeline %d", pipeline);
+    c->pipeline = pipeline;
+    return RPT_OK;
+}
+
+extern "C" int rpt_set_wave_slots(rpt_context* c, uint32_t slots) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    c->wave_slots = slots == 0 ? (1u << 21) : slots;
+    return RPT_OK;
+}
+
+// ============================================================================ scene
+extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices, uint32_t nvertices, const uint32_t* triangles,
+                                uint32_t ntriangles, const RptBVHNode* nodes, uint32_t nnodes, const RptMaterialData* materials,
+                                uint32_t nmaterials, const RptLightPickEntry* lights, uint32_t nlights, const uint8_t* atlas_rgba8,
+                                uint32_t atlas_w, uint32_t atlas_h, const float* sky_rgba32f, uint32_t sky_w, uint32_t sky_h) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    if (!vertices || !triangles || !nodes || !materials || !lights || nvertices == 0 || ntriangles == 0 || nnodes == 0 || nmaterials == 0 || nlights == 0)
+        return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: null or empty buffer");
+    if (ntriangles >= 0x80000000u) return c->fail(RPT_ERR_UNSUPPORTED, "more than 2^31 triangles");
+    if ((atlas_rgba8 && (atlas_w == 0 || atlas_h == 0)) || (sky_rgba32f && (sky_w == 0 || sky_h == 0)))
+        return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: image with a zero dimension");
+    for (size_t t = 0; t < (size_t)ntriangles; ++t)
+        if (triangles[4 * t + 3] >= nmaterials) return c->fail(RPT_ERR_INVALID_ARGUMENT, "triangle %zu references material %u of %u", t, triangles[4 * t + 3], nmaterials);
+    RPT_TRY(bind_device(c));
+    c->has_world = false;
+
+    // ---- private re-layout (host side, once per scene)
+    WideBvh wide;
+    const char* err = "";
+    if (!build_wide_bvh(nodes, nnodes, triangles, ntriangles, vertices, nvertices, wide, &err)) return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: %s", err);
+    if (wide.max_depth + 1 > kWideStackCapacity)
+        return c->fail(RPT_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%u)", wide.max_depth, kWideStackCapacity);
+
+    bool any_normal_map = false;
+    for (uint32_t m = 0; m < nmaterials; ++m) any_normal_map |= materials[m].has_normal_texture != 0;
+    const bool textured = [&] {
+        for (uint32_t m = 0; m < nmaterials; ++m)
+            if (materials[m].has_albedo_texture || materials[m].has_metallic_texture || materials[m].has_roughness_texture || materials[m].has_normal_texture) return true;
+        return false;
+    }();
+    if (textured && !atlas_rgba8) return c->fail(RPT_ERR_INVALID_ARGUMENT, "a material is textured but no atlas was supplied");
+
+    std::vector<float> shade((size_t)ntriangles * 16), tangent(any_normal_map ? (size_t)ntriangles * 12 : 0);
+    for (uint32_t wi = 0; wi < ntriangles; ++wi) {
+        const uint32_t* tri = triangles + 4 * (size_t)wide.orig_index[wi];
+        const RptPerVertexData &a = vertices[tri[0]], &b = vertices[tri[1]], &cc = vertices[tri[2]];
+        float* o = shade.data() + 16 * (size_t)wi;
+        o[0] = a.normal[0]; o[1] = a.normal[1]; o[2] = a.normal[2]; o[3] = a.uv0[0];
+        o[4] = b.normal[0]; o[5] = b.normal[1]; o[6] = b.normal[2]; o[7] = a.uv0[1];
+        o[8] = cc.normal[0]; o[9] = cc.normal[1]; o[10] = cc.normal[2]; o[11] = b.uv0[0];
+        o[12] = b.uv0[1]; o[13] = cc.uv0[0]; o[14] = cc.uv0[1]; o[15] = 0.0f;
+        if (any_normal_map) {
+            float* tg = tangent.data() + 12 * (size_t)wi;
+            for (int k = 0; k < 3; ++k) { tg[k] = a.tangent[k]; tg[4 + k] = b.tangent[k]; tg[8 + k] = cc.tangent[k]; }
+            tg[3] = tg[7] = tg[11] = 0.0f;
+        }
+    }
+
+    // light-pick table -> bins over compact light records (a one-entry table with ratio < 0 is the sentinel)
+    std::vector<LightBin> bins;
+    std::vector<LightRecord> records;
+    if (!(nlights == 1 && lights[0].ratio < 0.0f)) {
+        std::unordered_map<uint32_t, uint32_t> record_of;
+        auto record = [&](uint32_t tri_index, float area, float pdf, int& status) -> uint32_t {
+            auto it = record_of.find(tri_index);
+            if (it != record_of.end()) return it->second;
+            if (tri_index >= ntriangles) { status = RPT_ERR_INVALID_ARGUMENT; return 0; }
+            const uint32_t* tri = triangles + 4 * (size_t)tri_index;
+            const RptPerVertexData &a = vertices[tri[0]], &b = vertices[tri[1]], &cc = vertices[tri[2]];
+            LightRecord r{};
+            r.a_area = make_float4(a.vertex[0], a.vertex[1], a.vertex[2], area);
+            r.e1_pdf = make_float4(b.vertex[0] - a.vertex[0], b.vertex[1] - a.vertex[1], b.vertex[2] - a.vertex[2], pdf);
+            uint32_t wi = wide.wide_index[tri_index];
+            float wbits;
+            std::memcpy(&wbits, &wi, 4);
+            r.e2_tri = make_float4(cc.vertex[0] - a.vertex[0], cc.vertex[1] - a.vertex[1], cc.vertex[2] - a.vertex[2], wbits);
+            r.normal = make_float4(((a.normal[0] + b.normal[0]) + cc.normal[0]) / 3.0f, ((a.normal[1] + b.normal[1]) + cc.normal[1]) / 3.0f,
+                                   ((a.normal[2] + b.normal[2]) + cc.normal[2]) / 3.0f, 0.0f);
+            const float* em = materials[tri[3]].emissive;
+            r.emission = make_float4(em[0], em[1], em[2], 0.0f);
+            const uint32_t id = (uint32_t)records.size();
+            records.push_back(r);
+            record_of.emplace(tri_index, id);
+            return id;
+        };
+        int status = RPT_OK;
+        bins.reserve(nlights);
+        for (uint32_t i = 0; i < nlights; ++i) {
+            const RptLightPickEntry& e = lights[i];
+            LightBin bin{};
+            bin.light_a = record(e.triangle_index_a, e.triangle_area_a, e.triangle_pick_pdf_a, status);
+            // entries that were never topped up keep index_b = 0 with probability_b = 0: ratio == 1, never picked
+            bin.light_b = e.ratio >= 1.0f ? bin.light_a : record(e.triangle_index_b, e.triangle_area_b, e.triangle_pick_pdf_b, status);
+            bin.ratio = e.ratio;
+            bins.push_back(bin);
+        }
+        if (status != RPT_OK) return c->fail(status, "light-pick table references a triangle out of range");
+    }
+
+    // ---- uploads
+    cudaStream_t s = c->stream;
+    RPT_CUDA(c, c->d_vertices.upload(vertices, nvertices, s));
+    RPT_CUDA(c, c->d_triangles.upload(reinterpret_cast<const uint4*>(triangles), ntriangles, s));
+    RPT_CUDA(c, c->d_nodes.upload(nodes, nnodes, s));
+    RPT_CUDA(c, c->d_materials.upload(materials, nmaterials, s));
+    RPT_CUDA(c, c->d_lights.upload(lights, nlights, s));
+    RPT_CUDA(c, c->d_wide_nodes.upload(reinterpret_cast<const uint4*>(wide.nodes.data()), wide.nodes.size() * 5, s));
+    RPT_CUDA(c, c->d_tri_pos.upload(reinterpret_cast<const float4*>(wide.tri_pos.data()), (size_t)ntriangles * 3, s));
+    RPT_CUDA(c, c->d_tri_shade.upload(reinterpret_cast<const float4*>(shade.data()), (size_t)ntriangles * 4, s));
+    if (any_normal_map) RPT_CUDA(c, c->d_tri_tangent.upload(reinterpret_cast<const float4*>(tangent.data()), (size_t)ntriangles * 3, s));
+    else c->d_tri_tangent.release();
+    c->d_light_bins.release();
+    c->d_light_records.release();
+    if (!bins.empty()) {
+        RPT_CUDA(c, c->d_light_bins.upload(bins.data(), bins.size(), s));
+        RPT_CUDA(c, c->d_light_records.upload(records.data(), records.size(), s));
+    }
+    c->nbins = (uint32_t)bins.size();
+    const uchar4 white = make_uchar4(255, 255, 255, 255);
+    if (atlas_rgba8) {
+        RPT_CUDA(c, c->d_atlas.upload(reinterpret_cast<const uchar4*>(atlas_rgba8), (size_t)atlas_w * atlas_h, s));
+        c->atlas_w = atlas_w; c->atlas_h = atlas_h;
+    } else {
+        RPT_CUDA(c, c->d_atlas.upload(&white, 1, s));
+        c->atlas_w = c->atlas_h = 1;
+    }
+    const float magenta[16] = {1, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1};  // fallback_gpu_image, src/asset.rs:275-281
+    if (sky_rgba32f) {
+        RPT_CUDA(c, c->d_sky.upload(reinterpret_cast<const float4*>(sky_rgba32f), (size_t)sky_w * sky_h, s));
+        c->sky_w = sky_w; c->sky_h = sky_h;
+    } else {
+        RPT_CUDA(c, c->d_sky.upload(reinterpret_cast<const float4*>(magenta), 4, s));
+        c->sky_w = c->sky_h = 2;
+    }
+    RPT_CUDA(c, cudaStreamSynchronize(s));  // host staging vectors die at return
+    c->nlights = nlights;
+    c->nmaterials = nmaterials;
+    c->has_world = true;
+    return RPT_OK;
+}
+
+// ============================================================================ render state
+extern "C" int rpt_set_config(rpt_context* c, const RptTracingConfig* cfg) {
+    if (!c || !cfg) return RPT_ERR_INVALID_ARGUMENT;
+    if (cfg->width == 0 || cfg->height == 0 || (uint64_t)cfg->width * cfg->height > 0x7FFFFFFFull)
+        return c->fail(RPT_ERR_INVALID_ARGUMENT, "bad frame size %ux%u", cfg->width, cfg->height);
+    const uint32_t dims = rng_dimension_budget(*cfg);
+    if (dims > 31)
+        return c->fail(RPT_ERR_RNG_DIMENSIONS, "config can consume %u R-sequence dimensions per path; the reference's table has 31 (kernels/src/rng.rs:19-27)", dims);
+    RPT_TRY(bind_device(c));
+    const bool resized = !c->has_config || cfg->width != c->config.width || cfg->height != c->config.height;
+    c->config = *cfg;
+    c->has_config = true;
+    float m[9];
+    rpt_camera_matrix(cfg->cam_rotation[0], cfg->cam_rotation[1], m);
+    c->camera.position = mk3(cfg->cam_position[0], cfg->cam_position[1], cfg->cam_position[2]);
+    c->camera.c0 = mk3(m[0], m[1], m[2]);
+    c->camera.c1 = mk3(m[3], m[4], m[5]);
+    c->camera.c2 = mk3(m[6], m[7], m[8]);
+    c->camera.width = (float)cfg->width;
+    c->camera.height = (float)cfg->height;
+    c->camera.aspect = (float)cfg->height / (float)cfg->width;
+    const float yaw = std::atan2(cfg->sun_direction[2], cfg->sun_direction[0]);  // lib.rs:71
+    c->sky_yaw_sin = std::sin(yaw);
+    c->sky_yaw_cos = std::cos(yaw);
+    if (resized) {
+        const size_t n = (size_t)cfg->width * cfg->height;
+        RPT_CUDA(c, c->d_rng.alloc(n));
+        RPT_CUDA(c, c->d_output.alloc(n));
+        RPT_CUDA(c, cudaMemsetAsync(c->d_output.p, 0, n * sizeof(float4), c->stream));
+        c->d_rgb.release();
+        c->d_ids.release();
+        c->rng_written = false;
+        RPT_TRY(rebuild_pixel_map(c));
+    }
+    return RPT_OK;
+}
+
+extern "C" int rpt_write_rng(rpt_context* c, const uint32_t* seeds, size_t npixels) {
+    if (!c || !seeds) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "rpt_write_rng before rpt_set_config");
+    if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "rng has %zu entries, frame has %u pixels", npixels, c->npixels());
+    RPT_TRY(bind_device(c));
+    RPT_CUDA(c, cudaMemcpyAsync(c->d_rng.p, seeds, npixels * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    RPT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->rng_written = true;
+    return RPT_OK;
+}
+
+extern "C" int rpt_read_rng(rpt_context* c, uint32_t* seeds, size_t npixels) {
+    if (!c || !seeds) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->has_config || !c->rng_written) return c->fail(RPT_ERR_NOT_READY, "rng not written yet");
+    if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "rng has %u entries, caller asked for %zu", c->npixels(), npixels);
+    RPT_TRY(bind_device(c));
+    RPT_CUDA(c, cudaMemcpyAsync(seeds, c->d_rng.p, npixels * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+    return c->cuda(cudaStreamSynchronize(c->stream), "rpt_read_rng");
+}
+
+extern "C" int rpt_write_output(rpt_context* c, const float* rgba, size_t npixels) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "rpt_write_output before rpt_set_config");
+    if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "output has %zu entries, frame has %u pixels", npixels, c->npixels());
+    RPT_TRY(bind_device(c));
+    if (rgba) RPT_CUDA(c, cudaMemcpyAsync(c->d_output.p, rgba, npixels * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    else RPT_CUDA(c, cudaMemsetAsync(c->d_output.p, 0, npixels * sizeof(float4), c->stream));
+    return c->cuda(cudaStreamSynchronize(c->stream), "rpt_write_output");
+}
+
+extern "C" int rpt_set_tile_partition(rpt_context* c, uint32_t tile_rank, uint32_t tile_count) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    if (tile_count == 0 || tile_rank >= tile_count) return c->fail(RPT_ERR_INVALID_ARGUMENT, "tile rank %u of %u", tile_rank, tile_count);
+    RPT_TRY(bind_device(c));
+    c->tile_rank = tile_rank;
+    c->tile_count = tile_count;
+    return rebuild_pixel_map(c);
+}
+
+// ============================================================================ run
+extern "C" int rpt_enqueue(rpt_context* c, uint32_t n_samples) {
+    RPT_TRY(check_ready(c));
+    if (n_samples == 0) return RPT_OK;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    RPT_CUDA(c, cudaEventCreate(&e0));
+    RPT_CUDA(c, cudaEventCreate(&e1));
+    RPT_CUDA(c, cudaEventRecord(e0, c->stream));
+    int status = RPT_OK;
+    if (c->pipeline == RPT_PIPELINE_MEGAKERNEL) {
+        c->launch(RPT_STAGE_MEGAKERNEL, [&] { launch_mega_trace(mega_params(c), n_samples, c->stream); });
+        status = c->cuda(cudaGetLastError(), "megakernel launch");
+        // the megakernel counts its rays on the device; finished paths are counted here
+        if (status == RPT_OK) c->mega_paths += (uint64_t)(c->tile_count > 1 ? c->pixel_map_len : c->npixels()) * n_samples;
+    } else {
+        status = for_each_wave(c, n_samples, [&](const WaveDesc& d) { return run_wave(c, d, false, nullptr); });
+    }
+    cudaEventRecord(e1, c->stream);
+    c->timed.emplace_back(e0, e1);
+    return status;
+}
+
+extern "C" int rpt_sync(rpt_context* c) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    RPT_TRY(bind_device(c));
+    return c->cuda(cudaStreamSynchronize(c->stream), "rpt_sync");
+}
+
+// ============================================================================ readback
+extern "C" int rpt_read_output(rpt_context* c, float* rgba, size_t npixels) {
+    if (!c || !rgba) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "rpt_read_output before rpt_set_config");
+    if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "frame has %u pixels, caller asked for %zu", c->npixels(), npixels);
+    RPT_TRY(bind_device(c));
+    RPT_CUDA(c, cudaMemcpyAsync(rgba, c->d_output.p, npixels * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    return c->cuda(cudaStreamSynchronize(c->stream), "rpt_read_output");
+}
+
+extern "C" int rpt_read_framebuffer(rpt_context* c, float* rgb, size_t npixels, float samples) {
+    if (!c || !rgb) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "rpt_read_framebuffer before rpt_set_config");
+    if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "frame has %u pixels, caller asked for %zu", c->npixels(), npixels);
+    RPT_TRY(bind_device(c));
+    if (c->d_rgb.n != npixels * 3) RPT_CUDA(c, c->d_rgb.alloc(npixels * 3));
+    launch_normalize(c->d_output.p, c->d_rgb.p, (uint32_t)npixels, samples, c->stream);
+    c->kernel_launches++;
+    RPT_CUDA(c, cudaGetLastError());
+    RPT_CUDA(c, cudaMemcpyAsync(rgb, c->d_rgb.p, npixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    return c->cuda(cudaStreamSynchronize(c->stream), "rpt_read_framebuffer");
+}
+
+extern "C" int rpt_read_primary_ids(rpt_context* c, uint32_t* ids, size_t npixels) {
+    RPT_TRY(check_ready(c));
+    if (!ids) return RPT_ERR_INVALID_ARGUMENT;
+    if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "frame has %u pixels, caller asked for %zu", c->npixels(), npixels);
+    if (c->d_ids.n != npixels) RPT_CUDA(c, c->d_ids.alloc(npixels));
+    RPT_CUDA(c, cudaMemsetAsync(c->d_ids.p, 0xFF, npixels * sizeof(uint32_t), c->stream));
+    // counters must not move for a diagnostic pass: save and restore them around it
+    unsigned long long saved[4];
+    RPT_CUDA(c, cudaMemcpyAsync(saved, c->d_counters.p, sizeof saved, cudaMemcpyDeviceToHost, c->stream));
+    RPT_CUDA(c, cudaStreamSynchronize(c->stream));
+    int status = RPT_OK;
+    if (c->pipeline == RPT_PIPELINE_MEGAKERNEL) {
+        launch_mega_primary(mega_params(c), c->d_ids.p, c->stream);
+        c->kernel_launches++;
+        status = c->cuda(cudaGetLastError(), "primary-id launch");
+    } else {
+        status = for_each_wave(c, 1, [&](const WaveDesc& d) {
+            WaveDesc one = d;
+            one.k_samples = 1;
+            return run_wave(c, one, true, c->d_ids.p);
+        });
+    }
+    RPT_TRY(status);
+    RPT_CUDA(c, cudaMemcpyAsync(c->d_counters.p, saved, sizeof saved, cudaMemcpyHostToDevice, c->stream));
+    RPT_CUDA(c, cudaMemcpyAsync(ids, c->d_ids.p, npixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    return c->cuda(cudaStreamSynchronize(c->stream), "rpt_read_primary_ids");
+}
+
+extern "C" int rpt_get_counters(rpt_context* c, RptCounters* out) {
+    if (!c || !out) return RPT_ERR_INVALID_ARGUMENT;
+    RPT_TRY(bind_device(c));
+    unsigned long long host[4] = {0, 0, 0, 0};
+    RPT_CUDA(c, cudaMemcpyAsync(host, c->d_counters.p, sizeof host, cudaMemcpyDeviceToHost, c->stream));
+    RPT_CUDA(c, cudaStreamSynchronize(c->stream));
+    out->paths = host[0] + c->mega_paths;
+    out->nearest_rays = host[1];
+    out->any_rays = host[2];
+    out->kernel_launches = c->kernel_launches;
+    return RPT_OK;
+}
+
+extern "C" int rpt_reset_counters(rpt_context* c) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    RPT_TRY(bind_device(c));
+    RPT_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    RPT_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto& ev : c->timed) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    c->timed.clear();
+    c->device_ms = 0.0f;
+    c->kernel_launches = 0;
+    c->mega_paths = 0;
+    return RPT_OK;
+}
+
+extern "C" int rpt_get_device_ms(rpt_context* c, float* ms) {
+    if (!c || !ms) return RPT_ERR_INVALID_ARGUMENT;
+    RPT_TRY(bind_device(c));
+    RPT_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto& ev : c->timed) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, ev.first, ev.second) == cudaSuccess) c->device_ms += t;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    c->timed.clear();
+    *ms = c->device_ms;
+    return RPT_OK;
+}
+
+extern "C" int rpt_set_stage_timing(rpt_context* c, int enable) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    c->stage_timing = enable != 0;
+    return RPT_OK;
+}
+
+extern "C" int rpt_get_stage_timing(rpt_context* c, RptStageTiming* out) {
+    if (!c || !out) return RPT_ERR_INVALID_ARGUMENT;
+    RPT_TRY(bind_device(c));
+    RPT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->drain_stage_events();
+    *out = c->stage_totals;
+    c->stage_totals = RptStageTiming{};
+    return RPT_OK;
+}
+
+// ============================================================================ multi-GPU combine
+extern "C" int rpt_comm_unique_id(uint8_t* id_bytes_128) {
+    if (!id_bytes_128) return RPT_ERR_INVALID_ARGUMENT;
+    if (!g_nccl.load(g_create_error)) return RPT_ERR_NCCL;
+    NcclUniqueId id;
+    const int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) {
+        g_create_error = std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        return RPT_ERR_NCCL;
+    }
+    std::memcpy(id_bytes_128, id.internal, 128);
+    return RPT_OK;
+}
+
+extern "C" int rpt_comm_init(rpt_context* c, const uint8_t* id_bytes_128, int rank, int nranks) {
+    if (!c || !id_bytes_128 || nranks < 1 || rank < 0 || rank >= nranks) return RPT_ERR_INVALID_ARGUMENT;
+    if (!g_nccl.load(c->error)) return RPT_ERR_NCCL;
+    RPT_TRY(bind_device(c));
+    if (c->nccl_comm) { g_nccl.CommDestroy(c->nccl_comm); c->nccl_comm = nullptr; }
+    NcclUniqueId id;
+    std::memcpy(id.internal, id_bytes_128, 128);
+    const int r = g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank);
+    if (r != 0) return c->fail(RPT_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    c->nccl_rank = rank;
+    c->nccl_nranks = nranks;
+    return RPT_OK;
+}
+
+extern "C" int rpt_comm_reduce_output(rpt_context* c, int root) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->nccl_comm) return c->fail(RPT_ERR_NOT_READY, "rpt_comm_reduce_output before rpt_comm_init");
+    if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "no frame to reduce");
+    RPT_TRY(bind_device(c));
+    // per-GPU accumulators (sum rgb, sample count in w) add up to the single-GPU accumulator; in place on root
+    const int r = g_nccl.Reduce(c->d_output.p, c->d_output.p, (size_t)c->npixels() * 4, /*ncclFloat32*/ 7, /*ncclSum*/ 0, root, c->nccl_comm, c->stream);
+    if (r != 0) return c->fail(RPT_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    return RPT_OK;
+}
+
+extern "C" int rpt_comm_destroy(rpt_context* c) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    if (c->nccl_comm) {
+        bind_device(c);
+        cudaStreamSynchronize(c->stream);
+        g_nccl.CommDestroy(c->nccl_comm);
+        c->nccl_comm = nullptr;
+    }
+    return RPT_OK;
+}

@@ -17,7 +17,7 @@
 
 namespace rpt {
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 RPT_D uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 RPT_D int highest_bit(uint32_t v) { return 31 - __clz((int)v); }
 RPT_D int popcount(uint32_t v) { return __popc(v); }

@@ -1,0 +1,122 @@
+// device_scene.h — parameter blocks passed by value to the kernels, and the launch wrappers
+// the context (context.cu) calls.  All pointers are device pointers owned by the context.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "dev/shading.cuh"
+#include "dev/wide_bvh.cuh"
+
+namespace rpt {
+
+// Per-config constants (rpt_set_config) + read-only images.
+struct FrameParams {
+    Camera camera;
+    uint32_t width, height, min_bounces, max_bounces, nee, has_skybox;
+    float clamp_lo, clamp_hi;
+    f3 sun_dir;
+    float sun_intensity;
+    SkyImage sky;
+    Atlas atlas;
+    uint32_t tile_rank, tile_count;  // 32x32-tile round-robin partition (tile_count <= 1: whole frame)
+};
+
+// ---- megakernel arm: reads the reference's own layouts ---------------------------------------
+struct MegaParams {
+    Camera camera;
+    uint32_t width, height, min_bounces, max_bounces, nee, has_skybox;
+    float clamp_lo, clamp_hi;
+    f3 sun_dir;
+    float sun_intensity;
+    SkyImage sky;
+    const uchar4* atlas;
+    uint32_t atlas_w, atlas_h;
+    const float4* nodes;
+    const uint4* triangles;
+    const float4* vertices;
+    const RptMaterialData* materials;
+    const RptLightPickEntry* lights;
+    uint32_t nlights;
+    uint2* rng;
+    float4* output;
+    unsigned long long* counters;  // [0] paths, [1] nearest rays, [2] any rays
+    uint32_t tile_rank, tile_count;
+};
+
+void launch_mega_trace(const MegaParams& p, uint32_t n_samples, cudaStream_t stream);
+void launch_mega_primary(const MegaParams& p, uint32_t* ids, cudaStream_t stream);
+
+// ---- wavefront arm: private layouts ----------------------------------------------------------
+// One emissive triangle, in the order the light-pick table refers to it.
+struct LightRecord {
+    float4 a_area;        // vertex a, triangle area (LightPickEntry.triangle_area_*)
+    float4 e1_pdf;        // edge b-a, pick pdf (LightPickEntry.triangle_pick_pdf_*)
+    float4 e2_tri;        // edge c-a, bits(wide triangle index)
+    float4 normal;        // mean of the three vertex normals (light_pick.rs:128)
+    float4 emission;      // material emissive rgb
+};
+// LightPickEntry with triangle indices replaced by LightRecord indices.
+struct LightBin {
+    uint32_t light_a, light_b;
+    float ratio;
+};
+
+struct WideWorld {
+    WideScene bvh;                     // nodes + triangle position stream
+    const float4* tri_shade;           // 4 per triangle
+    const float4* tri_tangent;         // 3 per triangle, or null when no material is normal-mapped
+    const RptMaterialData* materials;
+    uint32_t nmaterials;
+    const LightBin* light_bins;        // null / nbins == 0: the "no lights" sentinel
+    uint32_t nbins;
+    const LightRecord* lights;
+};
+
+struct WaveCtl {
+    uint32_t n_ext[2];  // rays queued for the current / next extend pass
+    uint32_t n_hit, n_miss, n_shadow;
+    uint32_t pad[3];
+};
+
+// Path state of one wave, structure-of-arrays over `slots` path slots.
+struct WaveState {
+    float4* ray_o;   // origin.xyz, -
+    float4* ray_d;   // direction.xyz, bits(rng dimension | last lobe << 8)
+    float4* thr;     // throughput.xyz, pdf of the last BSDF sample
+    float4* rad;     // radiance of this pixel-sample so far
+    float4* mis_a;   // last BSDF spectrum.xyz, bits(light record sampled by NEE)
+    float4* mis_b;   // throughput before the last bounce .xyz, bits(wide triangle of that light)
+    uint2* hit;      // bits(t), wide triangle | backface << 31
+    float4* sh_o;    // shadow queue: origin.xyz, max_t
+    float4* sh_d;    //               direction.xyz, bits(slot)
+    float4* sh_c;    //               contribution.xyz if unoccluded
+    uint32_t* q_ext[2];
+    uint32_t* q_hit;
+    uint32_t* q_miss;
+    WaveCtl* ctl;
+    unsigned long long* counters;  // [0] paths, [1] nearest rays, [2] any rays
+};
+
+// Which pixel-samples a wave covers: slot = k * npix + j  ->  pixel = map(pix_base + j), sample k.
+struct WaveDesc {
+    uint32_t pix_base, npix, k_samples;
+    const uint32_t* pixel_map;  // null: identity
+};
+
+struct WaveLaunch {
+    int grid;  // persistent grid size (multiple of the SM count)
+    cudaStream_t stream;
+};
+
+void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole);
+void launch_wf_generate(const WaveLaunch& l, const FrameParams& f, const WaveState& s, const WaveDesc& d, const uint2* rng);
+void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, int in_queue, bool identity_queue, uint32_t n_identity);
+void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState& s);
+void launch_wf_export_primary(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, const WaveDesc& d, uint32_t* ids);
+void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld& w, const WaveState& s, const WaveDesc& d, const uint2* rng,
+                     uint32_t bounce, int out_queue);
+void launch_wf_miss(const WaveLaunch& l, const FrameParams& f, const WaveState& s);
+void launch_wf_accumulate(const WaveLaunch& l, const WaveState& s, const WaveDesc& d, uint2* rng, float4* output);
+void launch_normalize(const float4* output, float* rgb, uint32_t npixels, float samples, cudaStream_t stream);
+
+}  // namespace rpt

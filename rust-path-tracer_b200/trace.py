@@ -1,0 +1,260 @@
+"""Host-side mirror of the reference's trace driver (src/trace.rs) over the CUDA backend.
+
+Same names and meaning as the Rust API so tests and benches read like the reference's:
+
+    state = setup_trace(128, 128, 32)                    # src/trace.rs:331-344
+    state.config.nee = 1                                 # NextEventEstimation::MultipleImportanceSampling
+    trace_gpu("tests/golden/scenes/FurnaceTest.npz", None, state)   # src/trace.rs:136-224
+    state.framebuffer                                    # packed RGB f32, output.xyz / samples
+
+`trace_gpu` keeps the reference loop's structure — batches of `sync_rate` samples, `samples`
+advanced per batch, readback + normalisation per batch, flush on `interacting | dirty` — but each
+batch is ONE `rpt_enqueue(sync_rate)` (the device loops over the samples) instead of
+`sync_rate` x (dispatch + poll).  There is no `trace_cpu` here: the CPU path of the reference is
+the oracle (oracle/), which is test infrastructure, not product.
+
+`Renderer` is the thin object over the C ABI (include/rpt_b200.h) that `trace_gpu`, the tests
+and bench.py share.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import capi
+from .capi import TracingConfig
+from .world import World, make_rng_seeds
+
+
+class Renderer:
+    """One CUDA tracing context (one GPU).  Raises capi.RptError on any failure."""
+
+    def __init__(self, device: int = 0, pipeline: int = capi.PIPELINE_WAVEFRONT):
+        self._lib = capi.lib()
+        self._ctx = C.c_void_p()
+        code = self._lib.rpt_create(C.c_int(device), C.byref(self._ctx))
+        capi.check(code, "rpt_create")
+        self.device = device
+        self._call("rpt_set_pipeline", C.c_int(pipeline))
+        self.npixels = 0
+
+    def _call(self, name, *args):
+        capi.check(getattr(self._lib, name)(self._ctx, *args), name, self._ctx)
+
+    def close(self):
+        if self._ctx:
+            self._lib.rpt_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene / state -------------------------------------------------------------------
+    def upload_world(self, world: World, skybox: np.ndarray | None = None):
+        """skybox: (H, W, 4) float32 lat-long texels or None (2x2 magenta fallback)."""
+        atlas = None if world.atlas is None else np.ascontiguousarray(world.atlas, np.uint8)
+        sky = None if skybox is None else np.ascontiguousarray(skybox, np.float32)
+        u32 = C.c_uint32
+        self._call(
+            "rpt_upload_world",
+            capi.ptr(world.per_vertex_buffer), u32(len(world.per_vertex_buffer)),
+            capi.ptr(world.index_buffer), u32(len(world.index_buffer)),
+            capi.ptr(world.nodes), u32(len(world.nodes)),
+            capi.ptr(world.material_data_buffer), u32(len(world.material_data_buffer)),
+            capi.ptr(world.light_pick_buffer), u32(len(world.light_pick_buffer)),
+            capi.ptr(atlas), u32(0 if atlas is None else atlas.shape[1]), u32(0 if atlas is None else atlas.shape[0]),
+            capi.ptr(sky), u32(0 if sky is None else sky.shape[1]), u32(0 if sky is None else sky.shape[0]),
+        )
+
+    def set_config(self, config: TracingConfig):
+        self._call("rpt_set_config", C.byref(config))
+        self.npixels = config.width * config.height
+
+    def set_pipeline(self, pipeline: int):
+        self._call("rpt_set_pipeline", C.c_int(pipeline))
+
+    def set_wave_slots(self, slots: int):
+        self._call("rpt_set_wave_slots", C.c_uint32(slots))
+
+    def set_tile_partition(self, rank: int, count: int):
+        self._call("rpt_set_tile_partition", C.c_uint32(rank), C.c_uint32(count))
+
+    def write_rng(self, seeds: np.ndarray):
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        self._call("rpt_write_rng", capi.ptr(seeds), C.c_size_t(seeds.size // 2))
+
+    def read_rng(self) -> np.ndarray:
+        out = np.empty((self.npixels, 2), np.uint32)
+        self._call("rpt_read_rng", capi.ptr(out), C.c_size_t(self.npixels))
+        return out
+
+    def write_output(self, rgba: np.ndarray | None):
+        if rgba is None:
+            self._call("rpt_write_output", None, C.c_size_t(self.npixels))
+        else:
+            rgba = np.ascontiguousarray(rgba, np.float32)
+            self._call("rpt_write_output", capi.ptr(rgba), C.c_size_t(rgba.size // 4))
+
+    # ---- run / read ----------------------------------------------------------------------
+    def enqueue(self, n_samples: int):
+        self._call("rpt_enqueue", C.c_uint32(n_samples))
+
+    def sync(self):
+        self._call("rpt_sync")
+
+    def read_output(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.npixels, 4), np.float32)
+        self._call("rpt_read_output", capi.ptr(out), C.c_size_t(self.npixels))
+        return out
+
+    def read_framebuffer(self, samples: float, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.npixels * 3, np.float32)
+        self._call("rpt_read_framebuffer", capi.ptr(out), C.c_size_t(self.npixels), C.c_float(samples))
+        return out
+
+    def read_primary_ids(self) -> np.ndarray:
+        out = np.empty(self.npixels, np.uint32)
+        self._call("rpt_read_primary_ids", capi.ptr(out), C.c_size_t(self.npixels))
+        return out
+
+    def counters(self) -> dict:
+        c = capi.Counters()
+        self._call("rpt_get_counters", C.byref(c))
+        return {"paths": c.paths, "nearest_rays": c.nearest_rays, "any_rays": c.any_rays, "kernel_launches": c.kernel_launches}
+
+    def reset_counters(self):
+        self._call("rpt_reset_counters")
+
+    def device_ms(self) -> float:
+        ms = C.c_float(0)
+        self._call("rpt_get_device_ms", C.byref(ms))
+        return ms.value
+
+    def set_stage_timing(self, enable: bool):
+        self._call("rpt_set_stage_timing", C.c_int(int(enable)))
+
+    def stage_timing(self) -> dict:
+        """{stage: (summed launch ms, launches)} since the last call (syncs)."""
+        t = capi.StageTiming()
+        self._call("rpt_get_stage_timing", C.byref(t))
+        return {name: (t.ms[i], t.launches[i]) for i, name in enumerate(capi.STAGES)}
+
+    # ---- multi-GPU -----------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        capi.check(capi.lib().rpt_comm_unique_id(buf), "rpt_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._call("rpt_comm_init", buf, C.c_int(rank), C.c_int(nranks))
+
+    def comm_reduce_output(self, root: int = 0):
+        self._call("rpt_comm_reduce_output", C.c_int(root))
+
+    def comm_destroy(self):
+        self._call("rpt_comm_destroy")
+
+
+class TracingState:
+    """src/trace.rs:40-92.  Atomics become plain attributes (single-writer in this mirror)."""
+
+    def __init__(self, width: int, height: int):
+        self.config = TracingConfig.default(width, height)
+        self.framebuffer = np.zeros(width * height * 3, np.float32)
+        self.running = False
+        self.samples = 0
+        self.denoise = False
+        self.sync_rate = 32
+        self.use_blue_noise = True
+        self.interacting = False
+        self.dirty = False
+        self._stop_at = None  # set by setup_trace: the watcher thread's threshold
+        self.lock = threading.Lock()
+
+    def _watch(self):
+        # the reference spawns a thread that clears `running` once `samples >= N`
+        # (src/trace.rs:335-341); evaluated inline here, i.e. an infinitely fast watcher
+        if self._stop_at is not None and self.samples >= self._stop_at:
+            self.running = False
+
+
+def setup_trace(width: int, height: int, samples: int) -> TracingState:
+    """Harness for synchronous tracing, src/trace.rs:331-344."""
+    state = TracingState(width, height)
+    state.running = True
+    state._stop_at = samples
+    state._watch()  # samples == 0 requested: the watcher stops the loop at once ("startup" benches)
+    return state
+
+
+def load_skybox(path: str | None) -> np.ndarray | None:
+    """`load_dynamic_image` + `dynamic_image_to_gpu_image::<Rgba32Float>` (src/asset.rs:238-264):
+    .npy (H,W,3|4 float32) or any PIL-readable image; returns (H,W,4) float32 or None."""
+    if path is None:
+        return None
+    try:
+        if path.endswith(".npy"):
+            img = np.load(path).astype(np.float32)
+        else:
+            from PIL import Image
+
+            img = np.asarray(Image.open(path).convert("RGB"), np.float32) / np.float32(255.0)
+    except (OSError, ValueError):
+        return None
+    if img.ndim != 3 or img.shape[2] not in (3, 4):
+        return None
+    if img.shape[2] == 3:
+        img = np.concatenate([img, np.ones(img.shape[:2] + (1,), np.float32)], axis=2)
+    return np.ascontiguousarray(img, np.float32)
+
+
+def trace_gpu(scene_path: str, skybox_path: str | None, state: TracingState, device: int = 0,
+              pipeline: int = capi.PIPELINE_WAVEFRONT, world: World | None = None) -> None:
+    """src/trace.rs:136-224 with the wgpu dispatch replaced by the CUDA backend."""
+    if world is None:
+        world = World.from_path(scene_path)
+        if world is None:
+            return  # `let Some(world) = ... else { return; }`
+    skybox = load_skybox(skybox_path)
+    width, height = state.config.width, state.config.height
+    seeds = make_rng_seeds(width, height, use_blue_noise=state.use_blue_noise)
+
+    with Renderer(device, pipeline) as r:
+        r.upload_world(world, skybox)
+        r.set_config(state.config)
+        r.write_rng(seeds)
+        # restore previous state ("continue previous", src/trace.rs:163-164)
+        if state.samples > 0:
+            init = np.concatenate([state.framebuffer.reshape(-1, 3), np.ones((width * height, 1), np.float32)], axis=1)
+            r.write_output(init * np.float32(state.samples))
+
+        while state.running:
+            finished = state.sync_rate
+            flush = state.interacting or state.dirty
+            r.enqueue(finished)
+            r.sync()
+            state.samples += finished
+            state._watch()
+            with state.lock:
+                r.read_framebuffer(float(state.samples), state.framebuffer)
+            if flush:  # src/trace.rs:216-222
+                state.dirty = False
+                state.samples = 0
+                r.set_config(state.config)
+                r.write_output(None)
+                r.write_rng(seeds)

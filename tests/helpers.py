@@ -1,0 +1,63 @@
+"""Shared helpers for the parity tests: fixture scenes, configs, comparison metrics."""
+from __future__ import annotations
+
+import functools
+import os
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCENE_DIR = os.path.join(REPO, "tests", "golden", "scenes")
+GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
+SCENES = ["FurnaceTest", "DarkCornell", "PBRTest", "VeachMIS"]
+
+
+@functools.lru_cache(maxsize=None)
+def world(name: str):
+    from rust_path_tracer_b200.world import World
+
+    w = World.from_path(os.path.join(SCENE_DIR, name + ".npz"))
+    assert w is not None, name
+    return w
+
+
+def config(width: int, height: int, nee: int = 0, **kw):
+    from rust_path_tracer_b200.capi import TracingConfig
+
+    cfg = TracingConfig.default(width, height)
+    cfg.nee = nee
+    for k, v in kw.items():
+        if isinstance(v, (list, tuple)):
+            getattr(cfg, k)[:] = v
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def seeds(width: int, height: int):
+    from rust_path_tracer_b200.world import make_rng_seeds
+
+    return make_rng_seeds(width, height, use_blue_noise=True)
+
+
+def mae(a: np.ndarray, b: np.ndarray):
+    """Mean absolute error over pixels and channels of two normalised linear RGB images; NaN pixels
+    are counted separately and excluded."""
+    a = np.asarray(a, np.float64).reshape(-1, 3)
+    b = np.asarray(b, np.float64).reshape(-1, 3)
+    bad = ~(np.isfinite(a).all(axis=1) & np.isfinite(b).all(axis=1))
+    return float(np.abs(a[~bad] - b[~bad]).mean()), int(bad.sum())
+
+
+def synthetic_sky(width: int = 64, height: int = 32, seed: int = 7) -> np.ndarray:
+    """Small deterministic lat-long HDR image (float4) with a bright disk."""
+    rs = np.random.default_rng(seed)
+    img = np.zeros((height, width, 4), np.float32)
+    v = np.linspace(0, 1, height, dtype=np.float32)[:, None]
+    img[..., 0] = 0.3 + 0.5 * v
+    img[..., 1] = 0.4 + 0.4 * v
+    img[..., 2] = 0.9 - 0.3 * v
+    img[..., :3] += rs.random((height, width, 3), dtype=np.float32) * 0.05
+    img[height // 4 : height // 4 + 3, width // 3 : width // 3 + 3, :3] = 40.0
+    img[..., 3] = 1.0
+    return img

@@ -1,0 +1,151 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star):
+  * primary-hit triangle ids bit-exact except a stated < 1e-4 fraction of grazing / edge hits;
+  * accumulated radiance: mean absolute error <= 1e-3 at matched spp and sample indices;
+  * FurnaceTest stays energy conserving (the reference's own known answer, tests/correctness_tests.rs).
+"""
+import numpy as np
+import pytest
+
+import helpers
+import oracle as oracle_mod
+from rust_path_tracer_b200 import capi
+from rust_path_tracer_b200.trace import Renderer, setup_trace, trace_gpu
+
+pytestmark = pytest.mark.gpu
+
+ID_MISMATCH_BUDGET = 1e-4   # stated fraction of grazing / edge hits allowed to differ
+MAE_TOLERANCE = 1e-3        # per-pixel radiance tolerance of the north star, linear RGB
+
+
+def render_cuda(world, cfg, seeds, spp, pipeline, skybox=None, wave_slots=0):
+    with Renderer(0, pipeline) as r:
+        r.upload_world(world, skybox)
+        r.set_config(cfg)
+        if wave_slots:
+            r.set_wave_slots(wave_slots)
+        r.write_rng(seeds)
+        ids = r.read_primary_ids()
+        r.enqueue(spp)
+        out = r.read_output()
+        rng = r.read_rng()
+        ctr = r.counters()
+    return out, rng, ids, ctr
+
+
+def render_oracle(world, cfg, seeds, spp, skybox=None):
+    scene = oracle_mod.OracleScene(world, skybox)
+    _, _, _, ids = oracle_mod.trace(cfg, scene, seeds, 1, want_primary_ids=True)
+    out, rng, ctr, _ = oracle_mod.trace(cfg, scene, seeds, spp)
+    return out, rng, ids, ctr
+
+
+CASES = [
+    # scene, width, height, spp, nee
+    ("FurnaceTest", 96, 96, 16, 0),
+    ("FurnaceTest", 96, 96, 16, 1),
+    ("DarkCornell", 128, 96, 64, 1),
+    ("DarkCornell", 128, 96, 64, 2),
+    ("DarkCornell", 128, 96, 32, 0),
+    ("PBRTest", 160, 88, 16, 0),
+    ("VeachMIS", 160, 88, 32, 1),
+]
+
+
+@pytest.mark.parametrize("pipeline", [capi.PIPELINE_WAVEFRONT, capi.PIPELINE_MEGAKERNEL], ids=["wavefront", "megakernel"])
+@pytest.mark.parametrize("scene,w,h,spp,nee", CASES)
+def test_matches_oracle(scene, w, h, spp, nee, pipeline):
+    world = helpers.world(scene)
+    cfg = helpers.config(w, h, nee)
+    seeds = helpers.seeds(w, h)
+    o_out, o_rng, o_ids, o_ctr = render_oracle(world, cfg, seeds, spp)
+    c_out, c_rng, c_ids, c_ctr = render_cuda(world, cfg, seeds, spp, pipeline)
+
+    # rng state and sample count advance exactly like the reference kernel (lib.rs:185,225-226)
+    np.testing.assert_array_equal(c_rng, o_rng)
+    np.testing.assert_array_equal(c_out[:, 3], np.full(w * h, float(spp), np.float32))
+
+    mismatch = float((c_ids != o_ids).mean())
+    if pipeline == capi.PIPELINE_MEGAKERNEL:
+        assert mismatch == 0.0, "the megakernel arm traverses in the reference's order: ids must be identical"
+    assert mismatch <= ID_MISMATCH_BUDGET, f"primary-hit id mismatch fraction {mismatch}"
+
+    err, bad = helpers.mae(c_out[:, :3] / spp, o_out[:, :3] / spp)
+    assert bad == int((~np.isfinite(o_out[:, :3]).all(axis=1)).sum()), "NaN pixels must match the CPU path's"
+    assert err <= MAE_TOLERANCE, f"MAE {err}"
+    assert c_ctr["paths"] == w * h * spp
+    assert c_ctr["nearest_rays"] == o_ctr["nearest_rays"] or abs(c_ctr["nearest_rays"] / o_ctr["nearest_rays"] - 1) < 2e-3
+
+
+def test_wave_batching_is_invisible():
+    """Samples-per-wave and pixel chunking must not change the result (same per-pixel sample order)."""
+    world = helpers.world("DarkCornell")
+    cfg = helpers.config(64, 48, 1)
+    seeds = helpers.seeds(64, 48)
+    ref, *_ = render_cuda(world, cfg, seeds, 8, capi.PIPELINE_WAVEFRONT)
+    for slots in (1024, 4096, 1 << 16):
+        out, *_ = render_cuda(world, cfg, seeds, 8, capi.PIPELINE_WAVEFRONT, wave_slots=slots)
+        np.testing.assert_array_equal(out, ref)
+
+
+def test_enqueue_splits_like_consecutive_dispatches():
+    world = helpers.world("FurnaceTest")
+    cfg = helpers.config(64, 64, 1)
+    seeds = helpers.seeds(64, 64)
+    with Renderer(0) as r:
+        r.upload_world(world)
+        r.set_config(cfg)
+        r.write_rng(seeds)
+        r.enqueue(3)
+        r.enqueue(5)
+        a = r.read_output()
+        r.write_rng(seeds)
+        r.write_output(None)
+        r.enqueue(8)
+        b = r.read_output()
+    np.testing.assert_array_equal(a, b)
+
+
+def test_hdr_sky_and_rotated_camera():
+    world = helpers.world("PBRTest")
+    sky = helpers.synthetic_sky()
+    cfg = helpers.config(128, 72, 0, has_skybox=1, cam_rotation=[0.1, 0.4, 0.0, 0.0], cam_position=[1.0, 2.0, -6.0, 0.0])
+    seeds = helpers.seeds(128, 72)
+    o_out, _, o_ids, _ = render_oracle(world, cfg, seeds, 16, sky)
+    for pipeline in (capi.PIPELINE_WAVEFRONT, capi.PIPELINE_MEGAKERNEL):
+        c_out, _, c_ids, _ = render_cuda(world, cfg, seeds, 16, pipeline, sky)
+        assert float((c_ids != o_ids).mean()) <= ID_MISMATCH_BUDGET
+        err, _ = helpers.mae(c_out[:, :3] / 16, o_out[:, :3] / 16)
+        assert err <= MAE_TOLERANCE, err
+
+
+@pytest.mark.parametrize("use_mis", [False, True])
+def test_furnace_known_answer(use_mis):
+    """tests/correctness_tests.rs:14-33 through the mirrored harness: 128x128, 32 spp, pixel (65,75)."""
+    size, coord, albedo, tolerance = 128, (65, 75), 0.8, 0.02
+    state = setup_trace(size, size, 32)
+    if use_mis:
+        state.config.nee = 1
+    trace_gpu(helpers.SCENE_DIR + "/FurnaceTest.npz", None, state)
+    frame = state.framebuffer
+    for c in range(3):
+        v = frame[(size * 3) * coord[1] + coord[0] * 3 + c] ** (1.0 / 2.2)
+        assert abs(v - albedo) < tolerance
+
+
+def test_error_codes():
+    world = helpers.world("DarkCornell")
+    with Renderer(0) as r:
+        with pytest.raises(capi.RptError) as e:
+            r.enqueue(1)
+        assert e.value.code == capi.ERR_NOT_READY
+        r.upload_world(world)
+        cfg = helpers.config(32, 32, 1, max_bounces=8)
+        with pytest.raises(capi.RptError) as e:
+            r.set_config(cfg)
+        assert e.value.code == capi.ERR_RNG_DIMENSIONS
+        r.set_config(helpers.config(32, 32, 0))
+        with pytest.raises(capi.RptError) as e:
+            r.write_rng(np.zeros((10, 2), np.uint32))
+        assert e.value.code == capi.ERR_SIZE_MISMATCH
