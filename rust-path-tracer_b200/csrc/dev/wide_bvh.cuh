@@ -19,6 +19,13 @@ namespace rpt {
 
 #if defined(__CUDACC__)
 RPT_D uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+// 0xFF in every byte whose bit 7 is set.  (__byte_perm masks selector nibbles to 3 bits, so the
+// sign-replicating form of PRMT is only reachable through PTX.)
+RPT_D uint32_t sign_extend_s8x4(uint32_t v) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, 0xBA98;" : "=r"(r) : "r"(v));
+    return r;
+}
 RPT_D int highest_bit(uint32_t v) { return 31 - __clz((int)v); }
 RPT_D int popcount(uint32_t v) { return __popc(v); }
 RPT_D float as_float(uint32_t v) { return __uint_as_float(v); }
@@ -29,12 +36,12 @@ inline uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) {
     uint32_t r = 0;
     for (int i = 0; i < 4; ++i) {
         const uint32_t sel = (s >> (4 * i)) & 0xF;
-        uint32_t byte = (uint32_t)(both >> (8 * (sel & 7))) & 0xFF;
-        if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        const uint32_t byte = (uint32_t)(both >> (8 * (sel & 7))) & 0xFF;  // like __byte_perm: 3-bit selectors
         r |= byte << (8 * i);
     }
     return r;
 }
+inline uint32_t sign_extend_s8x4(uint32_t v) { return ((v >> 7) & 0x01010101u) * 0xFFu; }
 inline int highest_bit(uint32_t v) { return 31 - __builtin_clz(v); }
 inline int popcount(uint32_t v) { return __builtin_popcount(v); }
 inline float as_float(uint32_t v) { float f; memcpy(&f, &v, 4); return f; }
@@ -81,7 +88,7 @@ RPT_D WideRay make_wide_ray(f3 o, f3 d) {
 RPT_D uint32_t test_four(uint32_t meta4, uint32_t oct_inv4, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz,
                          f3 adj, f3 org_near, f3 org_far, float best_t) {
     const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const uint32_t inner_mask4 = byte_perm(is_inner4 << 3, 0u, 0xBA98u);  // 0xFF per inner byte
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);  // 0xFF per inner byte
     const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
     uint32_t mask = 0;
