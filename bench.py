@@ -238,7 +238,7 @@ def run_b200(args):
         "config": {"workload": label, "scene": scene + " (fixture of the shipped .glb)", "width": cfg.width, "height": cfg.height,
                    "nee": cfg.nee, "min_bounces": cfg.min_bounces, "max_bounces": cfg.max_bounces, "spp_per_step": spp,
                    "pipeline": args.pipeline, "partition": f"sample-index range x{world_size} + ncclReduce" if world_size > 1 else "single GPU",
-                   "l2": "working set per step (path state %.0f MB) exceeds the 126 MB L2" % (152.0 * min(npix * spp, args.wave_slots or (1 << 21)) / 1e6)},
+                   "l2": "working set per step (path state %.0f MB) exceeds the 126 MB L2" % (152.0 * min(npix * spp, args.wave_slots or (1 << 22)) / 1e6)},
         "mrays_per_s": total_rays / job_s / 1e6,
         "wall_ms_per_step": 1e3 * wall_s / args.steps,
         "gpu_launches": ctr["kernel_launches"],

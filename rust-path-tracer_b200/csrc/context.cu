@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -89,7 +90,11 @@ struct rpt_context {
     cudaStream_t stream = nullptr;
     std::string error;
     int pipeline = RPT_PIPELINE_WAVEFRONT;
-    uint32_t wave_slots = 1u << 21;
+    uint32_t wave_slots = 1u << 22;
+    // trace-kernel tunables (defaults chosen on B200; RPT_* env vars override for sweeps)
+    int trace_blocks_per_sm = 8;
+    int refill_below = 20;
+    float postpone_frac = 0.0f;
 
     // scene, reference layouts (megakernel arm)
     DevBuf<RptPerVertexData> d_vertices;
@@ -310,7 +315,7 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
     const FrameParams f = frame_params(c);
     const WideWorld w = wide_world(c);
     const WaveState s = wave_state(c);
-    const WaveLaunch l{c->sm_count, c->stream};
+    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below, c->postpone_frac};
     const uint32_t nslots = d.npix * d.k_samples;
     c->launch(RPT_STAGE_OTHER, [&] { launch_wf_reset(l, s, 1, true); });
     c->launch(RPT_STAGE_GENERATE, [&] { launch_wf_generate(l, f, s, d, c->d_rng.p); });
@@ -386,6 +391,10 @@ extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
         return RPT_ERR_NO_DEVICE;
     }
     c->sm_count = prop.multiProcessorCount;
+    if (const char* v = getenv("RPT_TRACE_BLOCKS_PER_SM")) c->trace_blocks_per_sm = std::max(1, atoi(v));
+    if (const char* v = getenv("RPT_REFILL_BELOW")) c->refill_below = atoi(v);
+    if (const char* v = getenv("RPT_POSTPONE_FRAC")) c->postpone_frac = (float)atof(v);
+    if (const char* v = getenv("RPT_WAVE_SLOTS")) c->wave_slots = (uint32_t)std::max(1024, atoi(v));
     *out_ctx = c;
     return RPT_OK;
 }
@@ -420,7 +429,7 @@ extern "C" int rpt_set_pipeline(rpt_context* c, int pipeline) {
 
 extern "C" int rpt_set_wave_slots(rpt_context* c, uint32_t slots) {
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
-    c->wave_slots = slots == 0 ? (1u << 21) : slots;
+    c->wave_slots = slots == 0 ? (1u << 22) : slots;
     return RPT_OK;
 }
 

@@ -112,85 +112,124 @@ RPT_D uint32_t test_four(uint32_t meta4, uint32_t oct_inv4, uint32_t nx, uint32_
     return mask;
 }
 
+// ---- traversal as a resumable cursor -------------------------------------------------------
+// The per-ray state between steps.  A step is either one node visit (`visit_node`) or one
+// ray/triangle test (`test_triangle`); `advance` pops the next group.  The device kernels
+// interleave these steps across the lanes of a warp (triangle postponing, ray refill); the
+// plain loop `wide_intersect` below composes them for one ray.
+//   ngroup = (first child node, hits << 24 | inner-slot mask): child nodes still to visit
+//   tgroup = (first triangle, 24-bit mask): triangles still to test
+// Stack entries are groups of either kind; a popped entry without node hits is a triangle group.
+template <bool NEAREST>
+struct WideCursor {
+    WideRay ray;
+    float best_t;   // current culling bound: best hit so far (nearest) or max_t (any)
+    float max_t;
+    WideHit res;
+    uint2 ngroup, tgroup;
+
+    RPT_D void begin(f3 ro, f3 rd, float max_t_) {
+        res = WideHit{1000000.0f, 0u, false, false};
+        max_t = max_t_;
+        ray = make_wide_ray(ro, rd);
+        best_t = NEAREST ? res.t : fminf(max_t_, res.t);
+        ngroup = make_uint2(0u, 0x80000000u);  // the root, as "child bit 31 of a virtual parent"
+        tgroup = make_uint2(0u, 0u);
+        // a ray with a non-finite component hits nothing in the reference either (every slab test
+        // compares false); without this the NaN-ignoring min/max would visit every node
+        if (!(finite3(ro) && finite3(rd))) ngroup.y = 0u;
+    }
+    RPT_D bool has_nodes() const { return ngroup.y > 0x00FFFFFFu; }
+    RPT_D bool has_triangles() const { return tgroup.y != 0u; }
+
+    // Pops the nearest pending child of ngroup and tests its eight children.
+    template <class Stack>
+    RPT_D void visit_node(const WideScene& s, Stack& stack) {
+        const uint32_t oct_inv = ray.oct_inv4 & 7u;
+        const uint32_t hits = ngroup.y;
+        const int bit = highest_bit(hits);
+        ngroup.y &= ~(1u << bit);
+        if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
+        const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
+        const uint32_t rel = (uint32_t)popcount(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
+        const uint4* node = s.nodes + 5u * (size_t)(ngroup.x + rel);
+        const uint4 n0 = __ldg(node), n1 = __ldg(node + 1), n2 = __ldg(node + 2), n3 = __ldg(node + 3), n4 = __ldg(node + 4);
+
+        const f3 p = mk3(as_float(n0.x), as_float(n0.y), as_float(n0.z));
+        const f3 cell = mk3(as_float((n0.w & 0xFFu) << 23), as_float(((n0.w >> 8) & 0xFFu) << 23), as_float(((n0.w >> 16) & 0xFFu) << 23));
+        const f3 adj = cell * ray.idir;
+        // push the planes out by a few ulps of the coordinates involved, so that rounding in
+        // (p - o) * idir can never cull a box the exact arithmetic would enter
+        const f3 pad = mk3((fabsf(p.x) + fabsf(ray.o.x) + 256.0f * cell.x) * 4.8e-7f, (fabsf(p.y) + fabsf(ray.o.y) + 256.0f * cell.y) * 4.8e-7f,
+                           (fabsf(p.z) + fabsf(ray.o.z) + 256.0f * cell.z) * 4.8e-7f);
+        const f3 rel_o = p - ray.o;
+        const f3 apad = mk3(fabsf(ray.idir.x) * pad.x, fabsf(ray.idir.y) * pad.y, fabsf(ray.idir.z) * pad.z);
+        const f3 org = rel_o * ray.idir;
+        const f3 org_near = org - apad, org_far = org + apad;
+
+        const bool nx = ray.d.x < 0.0f, ny = ray.d.y < 0.0f, nz = ray.d.z < 0.0f;
+        // children 0..3 and 4..7: near/far byte words per axis depend on the ray's sign
+        uint32_t hitmask = test_four(n1.z, ray.oct_inv4, nx ? n3.z : n2.x, ny ? n4.x : n2.z, nz ? n4.z : n3.x, nx ? n2.x : n3.z,
+                                     ny ? n2.z : n4.x, nz ? n3.x : n4.z, adj, org_near, org_far, best_t);
+        hitmask |= test_four(n1.w, ray.oct_inv4, nx ? n3.w : n2.y, ny ? n4.y : n2.w, nz ? n4.w : n3.y, nx ? n2.y : n3.w,
+                             ny ? n2.w : n4.y, nz ? n3.y : n4.w, adj, org_near, org_far, best_t);
+        ngroup.x = n1.x;
+        ngroup.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
+        tgroup.x = n1.y;
+        tgroup.y = hitmask & 0x00FFFFFFu;
+    }
+    // ngroup holds no node hits: whatever it holds is a (postponed) triangle group.
+    RPT_D void take_triangle_group() {
+        tgroup = ngroup;
+        ngroup = make_uint2(0u, 0u);
+    }
+    // Tests the next pending triangle; returns true when an any-hit query is decided.
+    RPT_D bool test_triangle(const WideScene& s) {
+        const int k = highest_bit(tgroup.y);
+        tgroup.y &= ~(1u << k);
+        const uint32_t ti = tgroup.x + (uint32_t)k;
+        const float4* rec = s.tri_pos + 3u * (size_t)ti;
+        const float4 a = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
+        float t;
+        bool back;
+        if (ray_triangle(ray.o, ray.d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t, back) && t > 0.001f && t < res.t &&
+            (NEAREST || t <= max_t)) {
+            res.t = t;
+            res.triangle = ti;
+            res.hit = true;
+            res.backface = back;
+            if (!NEAREST) return true;
+            best_t = t;
+        }
+        return false;
+    }
+    // After the triangles: make sure ngroup holds work, popping the stack; false when the ray is done.
+    template <class Stack>
+    RPT_D bool advance(Stack& stack) {
+        if (ngroup.y <= 0x00FFFFFFu) {
+            if (stack.empty()) return false;
+            ngroup = stack.pop();
+        }
+        return true;
+    }
+};
+
 // Nearest hit (NEAREST = true, `t < best`) or any hit with t <= max_t (NEAREST = false), with the
 // reference's acceptance window t > 0.001 (intersection.rs:195).  Stack: push(uint2), pop(),
 // empty().
 template <bool NEAREST, class Stack>
 RPT_D WideHit wide_intersect(const WideScene& s, f3 ro, f3 rd, float max_t, Stack& stack) {
-    WideHit res{1000000.0f, 0u, false, false};
-    // a ray with a non-finite component hits nothing in the reference either (every slab test
-    // compares false); without this early-out the NaN-ignoring min/max would visit every node
-    if (!(finite3(ro) && finite3(rd))) return res;
-    const WideRay ray = make_wide_ray(ro, rd);
-    float best_t = NEAREST ? res.t : fminf(max_t, res.t);
-    const uint32_t oct_inv = ray.oct_inv4 & 7u;
-
-    uint2 ngroup = make_uint2(0u, 0x80000000u);  // the root, as "child bit 31 of a virtual parent"
-    uint2 tgroup = make_uint2(0u, 0u);
+    WideCursor<NEAREST> c;
+    c.begin(ro, rd, max_t);
+    if (!c.has_nodes()) return c.res;
     for (;;) {
-        if (ngroup.y > 0x00FFFFFFu) {
-            const uint32_t hits = ngroup.y;
-            const int bit = highest_bit(hits);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
-            const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
-            const uint32_t rel = (uint32_t)popcount(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
-            const uint4* node = s.nodes + 5u * (size_t)(ngroup.x + rel);
-            const uint4 n0 = __ldg(node), n1 = __ldg(node + 1), n2 = __ldg(node + 2), n3 = __ldg(node + 3), n4 = __ldg(node + 4);
-
-            const f3 p = mk3(as_float(n0.x), as_float(n0.y), as_float(n0.z));
-            const f3 cell = mk3(as_float((n0.w & 0xFFu) << 23), as_float(((n0.w >> 8) & 0xFFu) << 23), as_float(((n0.w >> 16) & 0xFFu) << 23));
-            const f3 adj = cell * ray.idir;
-            // push the planes out by a few ulps of the coordinates involved, so that rounding in
-            // (p - o) * idir can never cull a box the exact arithmetic would enter
-            const f3 pad = mk3((fabsf(p.x) + fabsf(ray.o.x) + 256.0f * cell.x) * 4.8e-7f, (fabsf(p.y) + fabsf(ray.o.y) + 256.0f * cell.y) * 4.8e-7f,
-                               (fabsf(p.z) + fabsf(ray.o.z) + 256.0f * cell.z) * 4.8e-7f);
-            const f3 rel_o = p - ray.o;
-            const f3 apad = mk3(fabsf(ray.idir.x) * pad.x, fabsf(ray.idir.y) * pad.y, fabsf(ray.idir.z) * pad.z);
-            const f3 org = rel_o * ray.idir;
-            const f3 org_near = org - apad, org_far = org + apad;
-
-            const bool nx = ray.d.x < 0.0f, ny = ray.d.y < 0.0f, nz = ray.d.z < 0.0f;
-            // children 0..3 and 4..7: near/far byte words per axis depend on the ray's sign
-            uint32_t hitmask = test_four(n1.z, ray.oct_inv4, nx ? n3.z : n2.x, ny ? n4.x : n2.z, nz ? n4.z : n3.x, nx ? n2.x : n3.z,
-                                         ny ? n2.z : n4.x, nz ? n3.x : n4.z, adj, org_near, org_far, best_t);
-            hitmask |= test_four(n1.w, ray.oct_inv4, nx ? n3.w : n2.y, ny ? n4.y : n2.w, nz ? n4.w : n3.y, nx ? n2.y : n3.w,
-                                 ny ? n2.w : n4.y, nz ? n3.y : n4.w, adj, org_near, org_far, best_t);
-
-            ngroup.x = n1.x;
-            ngroup.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
-            tgroup.x = n1.y;
-            tgroup.y = hitmask & 0x00FFFFFFu;
-        } else {
-            tgroup = ngroup;
-            ngroup = make_uint2(0u, 0u);
-        }
-
-        while (tgroup.y != 0u) {
-            const int k = highest_bit(tgroup.y);
-            tgroup.y &= ~(1u << k);
-            const uint32_t ti = tgroup.x + (uint32_t)k;
-            const float4* rec = s.tri_pos + 3u * (size_t)ti;
-            const float4 a = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
-            float t;
-            bool back;
-            if (ray_triangle(ro, rd, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t, back) && t > 0.001f && t < res.t &&
-                (NEAREST || t <= max_t)) {
-                res.t = t;
-                res.triangle = ti;
-                res.hit = true;
-                res.backface = back;
-                if (!NEAREST) return res;
-                best_t = t;
-            }
-        }
-
-        if (ngroup.y <= 0x00FFFFFFu) {
-            if (stack.empty()) break;
-            ngroup = stack.pop();
-        }
+        if (c.has_nodes()) c.visit_node(s, stack);
+        else c.take_triangle_group();
+        while (c.has_triangles())
+            if (c.test_triangle(s)) return c.res;
+        if (!c.advance(stack)) break;
     }
-    return res;
+    return c.res;
 }
 
 }  // namespace rpt

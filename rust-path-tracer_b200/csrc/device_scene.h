@@ -75,7 +75,8 @@ struct WideWorld {
 struct WaveCtl {
     uint32_t n_ext[2];  // rays queued for the current / next extend pass
     uint32_t n_hit, n_miss, n_shadow;
-    uint32_t pad[3];
+    uint32_t fetch_extend, fetch_shadow;  // work cursors of the persistent trace kernels
+    uint32_t pad;
 };
 
 // Path state of one wave, structure-of-arrays over `slots` path slots.
@@ -104,8 +105,11 @@ struct WaveDesc {
 };
 
 struct WaveLaunch {
-    int grid;  // persistent grid size (multiple of the SM count)
+    int grid;  // SM count: persistent grids are multiples of it
     cudaStream_t stream;
+    int trace_blocks_per_sm;  // resident 128-thread blocks per SM of the trace kernels
+    int refill_below;         // refill idle lanes once fewer than this many lanes of a warp hold a ray
+    float postpone_frac;      // postpone triangle tests while fewer than this fraction of live lanes have any
 };
 
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole);

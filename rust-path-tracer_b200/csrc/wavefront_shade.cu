@@ -204,9 +204,9 @@ __global__ void __launch_bounds__(kShadeBlock) wf_shade_kernel(FrameParams f, Wi
             s.sh_d[qb + rank] = mk4(sh_d, __uint_as_float(slot));
             s.sh_c[qb + rank] = mk4(sh_c, 0.0f);
         }
-        qb = warp_reserve(want_next, &s.ctl->n_ext[out_queue], rank);
+        qb = warp_reserve(want_next, out_queue ? &s.ctl->n_ext[1] : &s.ctl->n_ext[0], rank);
         if (want_next) {
-            s.q_ext[out_queue][qb + rank] = slot;
+            (out_queue ? s.q_ext[1] : s.q_ext[0])[qb + rank] = slot;
             s.ray_o[slot] = mk4(next_o, 0.0f);
             s.ray_d[slot] = mk4(next_d, __uint_as_float(next_flags));
             s.thr[slot] = mk4(next_thr, next_pdf);
@@ -247,8 +247,9 @@ __global__ void __launch_bounds__(256) wf_accumulate_kernel(WaveState s, WaveDes
 __global__ void wf_reset_kernel(WaveState s, int next_queue, bool whole) {
     if (threadIdx.x == 0) {
         s.ctl->n_hit = 0; s.ctl->n_miss = 0; s.ctl->n_shadow = 0;
-        s.ctl->n_ext[next_queue] = 0;
-        if (whole) s.ctl->n_ext[next_queue ^ 1] = 0;
+        s.ctl->fetch_extend = 0; s.ctl->fetch_shadow = 0;
+        if (whole || next_queue == 0) s.ctl->n_ext[0] = 0;
+        if (whole || next_queue == 1) s.ctl->n_ext[1] = 0;
     }
 }
 
@@ -263,11 +264,11 @@ __global__ void normalize_kernel(const float4* __restrict__ output, float* __res
 
 void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld& w, const WaveState& s, const WaveDesc& d, const uint2* rng,
                      uint32_t bounce, int out_queue) {
-    wf_shade_kernel<<<l.grid * 4, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce, out_queue);
+    wf_shade_kernel<<<l.grid * 6, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce, out_queue);
 }
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole) { wf_reset_kernel<<<1, 32, 0, l.stream>>>(s, next_queue, whole); }
 void launch_wf_miss(const WaveLaunch& l, const FrameParams& f, const WaveState& s) {
-    wf_miss_kernel<<<l.grid * 4, kShadeBlock, 0, l.stream>>>(f, s);
+    wf_miss_kernel<<<l.grid * 8, kShadeBlock, 0, l.stream>>>(f, s);
 }
 void launch_wf_accumulate(const WaveLaunch& l, const WaveState& s, const WaveDesc& d, uint2* rng, float4* output) {
     wf_accumulate_kernel<<<l.grid * 2, 256, 0, l.stream>>>(s, d, rng, output);

@@ -62,47 +62,105 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(FrameParams f, WaveSta
     }
 }
 
-__global__ void __launch_bounds__(kTraceBlock) wf_extend_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity) {
-    __shared__ uint2 slabs[kTraceWarps][kWideStackCapacity][32];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t n = identity ? n_identity : s.ctl->n_ext[in_queue];
-    const uint32_t* __restrict__ queue = s.q_ext[in_queue];
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.counters + 1, (unsigned long long)n);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    // whole warps iterate together so the ballots below always see 32 lanes
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
-        const uint32_t i = base + lane;
-        const bool active = i < n;
-        uint32_t slot = 0;
-        WideHit h{1000000.0f, 0u, false, false};
-        if (active) {
-            slot = identity ? i : __ldg(queue + i);
-            const float4 o = s.ray_o[slot], dv = s.ray_d[slot];
-            SmemStack st{&slabs[warp][0][lane], 0};
-            h = wide_intersect<true>(bvh, xyz(o), xyz(dv), 0.0f, st);
-            if (h.hit) s.hit[slot] = make_uint2(__float_as_uint(h.t), h.triangle | (h.backface ? 0x80000000u : 0u));
-        }
-        __syncwarp();
-        warp_append(active && h.hit, s.q_hit, &s.ctl->n_hit, slot);
-        warp_append(active && !h.hit, s.q_miss, &s.ctl->n_miss, slot);
-    }
-}
+// Persistent trace kernel for both ray kinds.
+//   NEAREST: items are path slots (queue q_ext[in_queue], or 0..n_identity-1 for bounce 0); the hit
+//            record goes to s.hit[slot] and the slot is appended to q_hit or q_miss.
+//   ANY:     items are shadow-queue entries; an unoccluded ray adds its contribution to rad[slot].
+// Lanes pull rays one at a time from a device-side cursor: when a lane's ray terminates it waits
+// only until the warp's live-lane count drops below `refill_below`, then every idle lane is handed
+// a new ray (ray refill keeps the warp full although rays need very different numbers of steps).
+// Inside the traversal loop a lane that reaches triangles while fewer than `postpone_frac` of the
+// live lanes have any pushes the triangle group back on its stack and goes on with nodes first
+// (triangle postponing), so ray/triangle tests execute with more lanes enabled.
 
-__global__ void __launch_bounds__(kTraceBlock) wf_shadow_kernel(WideScene bvh, WaveState s) {
+template <bool NEAREST>
+__global__ void __launch_bounds__(kTraceBlock) wf_trace_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
+                                                               int refill_below, float postpone_frac) {
     __shared__ uint2 slabs[kTraceWarps][kWideStackCapacity][32];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t n = s.ctl->n_shadow;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.counters + 2, (unsigned long long)n);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o = s.sh_o[i], dv = s.sh_d[i];
-        SmemStack st{&slabs[warp][0][lane], 0};
-        const WideHit h = wide_intersect<false>(bvh, xyz(o), xyz(dv), o.w, st);
-        if (!h.hit) {  // unoccluded: radiance += mask_nan(contribution) (lib.rs:164; masked when queued)
-            const uint32_t slot = __float_as_uint(dv.w);
-            const float4 c = s.sh_c[i];
-            float4 r = s.rad[slot];
-            r.x += c.x; r.y += c.y; r.z += c.z;
-            s.rad[slot] = r;
+    // (ternaries, not s.q_ext[in_queue]: dynamic indexing would force the parameter block into local memory)
+    const uint32_t n = NEAREST ? (identity ? n_identity : (in_queue ? s.ctl->n_ext[1] : s.ctl->n_ext[0])) : s.ctl->n_shadow;
+    const uint32_t* __restrict__ queue = in_queue ? s.q_ext[1] : s.q_ext[0];
+    uint32_t* fetch = NEAREST ? &s.ctl->fetch_extend : &s.ctl->fetch_shadow;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.counters + (NEAREST ? 1 : 2), (unsigned long long)n);
+
+    SmemStack st{&slabs[warp][0][lane], 0};
+    WideCursor<NEAREST> c;
+    uint32_t item = 0;       // path slot (NEAREST) / shadow-queue index (ANY)
+    bool busy = false;       // this lane holds an unfinished ray
+    bool publish = false;    // NEAREST: a finished ray waits for the warp-wide queue append
+    bool exhausted = false;  // the cursor ran past the end of the queue (warp-uniform)
+
+    for (;;) {
+        // ---- converged: publish finished rays, then refill idle lanes ------------------------
+        if (NEAREST) {
+            warp_append(publish && c.res.hit, s.q_hit, &s.ctl->n_hit, item);
+            warp_append(publish && !c.res.hit, s.q_miss, &s.ctl->n_miss, item);
+            publish = false;
+        }
+        if (!exhausted) {
+            const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !busy);
+            if (idle) {
+                const int leader = __ffs((int)idle) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                const uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                exhausted = base + (uint32_t)__popc(idle) >= n;
+                if (!busy && i < n) {
+                    float4 o, dv;
+                    float max_t = 0.0f;
+                    if (NEAREST) {
+                        item = identity ? i : __ldg(queue + i);
+                        o = s.ray_o[item];
+                        dv = s.ray_d[item];
+                    } else {
+                        item = i;
+                        o = s.sh_o[i];
+                        dv = s.sh_d[i];
+                        max_t = o.w;
+                    }
+                    c.begin(xyz(o), xyz(dv), max_t);
+                    st.n = 0;
+                    busy = true;
+                }
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, busy) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- traverse until the ray ends or the warp wants a refill ---------------------------
+        while (busy) {
+            bool finished = false;
+            if (c.has_nodes()) c.visit_node(bvh, st);
+            else c.take_triangle_group();
+            const int live = __popc(__activemask());
+            while (c.has_triangles()) {
+                if ((float)__popc(__activemask()) < postpone_frac * (float)live && (c.has_nodes() || !st.empty())) {
+                    st.push(c.tgroup);  // postponed: comes back through advance() / take_triangle_group()
+                    c.tgroup.y = 0u;
+                    break;
+                }
+                if (c.test_triangle(bvh)) { finished = true; break; }
+            }
+            if (!finished && !c.advance(st)) finished = true;
+            if (finished) {
+                busy = false;
+                if (NEAREST) {
+                    if (c.res.hit) s.hit[item] = make_uint2(__float_as_uint(c.res.t), c.res.triangle | (c.res.backface ? 0x80000000u : 0u));
+                    publish = true;
+                } else if (!c.res.hit) {  // unoccluded: radiance += mask_nan(contribution) (lib.rs:164; masked when queued)
+                    const uint32_t slot = __float_as_uint(s.sh_d[item].w);
+                    const float4 add = s.sh_c[item];
+                    float4 r = s.rad[slot];
+                    r.x += add.x; r.y += add.y; r.z += add.z;
+                    s.rad[slot] = r;
+                }
+                break;
+            }
+            if (!exhausted && __popc(__activemask()) < refill_below) break;
         }
     }
 }
@@ -126,10 +184,10 @@ void launch_wf_generate(const WaveLaunch& l, const FrameParams& f, const WaveSta
     wf_generate_kernel<<<l.grid * 2, 256, 0, l.stream>>>(f, s, d, rng);
 }
 void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, int in_queue, bool identity_queue, uint32_t n_identity) {
-    wf_extend_kernel<<<l.grid * 4, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity);
+    wf_trace_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.postpone_frac);
 }
 void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState& s) {
-    wf_shadow_kernel<<<l.grid * 4, kTraceBlock, 0, l.stream>>>(bvh, s);
+    wf_trace_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.postpone_frac);
 }
 void launch_wf_export_primary(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, const WaveDesc& d, uint32_t* ids) {
     wf_export_primary_kernel<<<(d.npix + 255) / 256, 256, 0, l.stream>>>(bvh, s, d, ids);

@@ -1,0 +1,90 @@
+"""The backend's 8-wide BVH collapse + traversal, compiled for the host by tests/cpu_harness, must
+return the same triangle, the same t bits and the same back-face flag as the reference traversal
+(oracle) — nearest-hit and any-hit — on camera rays and on random / axis-aligned / surface rays."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+import oracle as om
+
+HARNESS_DIR = os.path.join(helpers.REPO, "tests", "cpu_harness")
+HARNESS_SO = os.path.join(HARNESS_DIR, "_build", "libwide_harness.so")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    srcs = [os.path.join(HARNESS_DIR, "wide_harness.cpp"), os.path.join(helpers.REPO, "rust-path-tracer_b200", "csrc", "wide_bvh_build.cpp")]
+    hdrs = [os.path.join(helpers.REPO, "rust-path-tracer_b200", "csrc", "dev", h) for h in ("wide_bvh.cuh", "exact.cuh", "vec.cuh")]
+    os.makedirs(os.path.dirname(HARNESS_SO), exist_ok=True)
+    if not os.path.exists(HARNESS_SO) or any(os.path.getmtime(s) > os.path.getmtime(HARNESS_SO) for s in srcs + hdrs):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-o", HARNESS_SO, *srcs], check=True,
+                       capture_output=True)
+    return C.CDLL(HARNESS_SO)
+
+
+def wide_intersect(lib, world, rays, any_hit=False, max_t=None):
+    n = len(rays)
+    rays = np.ascontiguousarray(rays, np.float32)
+    max_t = np.zeros(n, np.float32) if max_t is None else np.ascontiguousarray(max_t, np.float32)
+    hit, tri, t, back = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
+    stats = np.zeros(5, np.uint32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.harness_wide_intersect(P(world.per_vertex_buffer), C.c_uint32(len(world.per_vertex_buffer)), P(world.index_buffer),
+                                    C.c_uint32(len(world.index_buffer)), P(world.nodes), C.c_uint32(len(world.nodes)), P(rays), C.c_uint32(n),
+                                    C.c_int(int(any_hit)), P(max_t), P(hit), P(tri), P(t), P(back), P(stats))
+    assert rc == 0
+    return hit, tri, t, back, stats
+
+
+def make_rays(world, n, rs):
+    pos = world.per_vertex_buffer["vertex"][:, :3]
+    lo, hi = pos.min(0), pos.max(0)
+    c, ext = (lo + hi) / 2, (hi - lo).max()
+    o = (c + (rs.random((n, 3)) - 0.5) * ext * 1.2).astype(np.float32)
+    d = rs.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    k = n // 20
+    d[:k, 0] = 0; d[k:2 * k, 1] = 0; d[2 * k:3 * k] = [0, 0, 1]; d[3 * k:4 * k] = [0, -1, 0]
+    tris = world.index_buffer
+    tp = pos[tris[rs.integers(0, len(tris), n // 2), :3]]
+    bw = rs.dirichlet([1, 1, 1], n // 2).astype(np.float32)
+    o[n // 2:] = (tp * bw[:, :, None]).sum(1) + d[n // 2:] * np.float32(0.001)  # bounce-like rays leaving a surface
+    return np.concatenate([o, d], axis=1).astype(np.float32), (rs.random(n) * ext).astype(np.float32)
+
+
+@pytest.mark.parametrize("scene", helpers.SCENES)
+def test_wide_traversal_matches_reference_traversal(harness, scene):
+    world = helpers.world(scene)
+    osc = om.OracleScene(world)
+    rays, max_t = make_rays(world, 40000, np.random.default_rng(3))
+    cfg = helpers.config(160, 90)
+    rays = np.concatenate([rays, om.camera_rays(cfg, helpers.seeds(160, 90))])
+    max_t = np.concatenate([max_t, np.full(160 * 90, 3.0, np.float32)])
+
+    oh, ot, ott, ob = om.intersect(osc, rays)
+    wh, wt, wtt, wb, stats = wide_intersect(harness, world, rays)
+    np.testing.assert_array_equal(wh, oh)
+    both = oh == 1
+    tie = both & (wt != ot)  # a different triangle is only acceptable as an exact-t tie
+    assert (wtt[tie].view(np.uint32) == ott[tie].view(np.uint32)).all()
+    assert tie.mean() <= 1e-4
+    np.testing.assert_array_equal(wtt[both & ~tie].view(np.uint32), ott[both & ~tie].view(np.uint32))
+    np.testing.assert_array_equal(wb[both & ~tie], ob[both & ~tie])
+    assert stats[4] <= 24 and stats[1] + 1 <= 24  # stack high-water / tree depth within the smem stack
+
+    oh, *_ = om.intersect(osc, rays, any_hit=True, max_t=max_t)
+    wh, *_ = wide_intersect(harness, world, rays, any_hit=True, max_t=max_t)
+    np.testing.assert_array_equal(wh, oh)
+
+
+def test_nan_and_degenerate_rays_miss(harness):
+    world = helpers.world("DarkCornell")
+    rays = np.array([[0, 1, -5, np.nan, 0, 1], [np.nan, 1, -5, 0, 0, 1], [0, 1, -5, 0, 0, 0], [0, 1, -5, np.inf, 0, 1]], np.float32)
+    oh, *_ = om.intersect(om.OracleScene(world), rays)
+    wh, *_ = wide_intersect(harness, world, rays)
+    np.testing.assert_array_equal(wh, oh)
+    assert (wh == 0).all()

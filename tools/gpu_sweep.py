@@ -1,0 +1,25 @@
+"""Scratch: time the wavefront stages for tunable settings (run on the GPU box).
+usage: python tools/gpu_sweep.py workload spp "ENV=VAL,ENV=VAL" ..."""
+import os, sys
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import numpy as np
+import bench
+from rust_path_tracer_b200.trace import Renderer
+
+workload, spp = sys.argv[1], int(sys.argv[2])
+world, cfg, seeds, _, label, scene = bench.load_workload(workload)
+for setting in sys.argv[3:] or [""]:
+    for kv in filter(None, setting.split(",")):
+        k, v = kv.split("=")
+        os.environ[k] = v
+    with Renderer(0) as r:
+        r.upload_world(world); r.set_config(cfg); r.write_rng(seeds)
+        r.enqueue(spp); r.sync()
+        r.reset_counters(); r.enqueue(spp); ms = r.device_ms(); c = r.counters()
+        r.set_stage_timing(True); r.enqueue(spp); st = r.stage_timing()
+    rays = c["nearest_rays"] + c["any_rays"]
+    print(f"{workload} [{setting}] {c['paths']/ms/1e3:8.1f} Mpaths/s {rays/ms/1e3:8.1f} Mrays/s | " +
+          " ".join(f"{k}={v[0]:.1f}" for k, v in st.items() if v[1]), flush=True)
+    for kv in filter(None, setting.split(",")):
+        os.environ.pop(kv.split("=")[0], None)
