@@ -68,6 +68,7 @@ struct WideHit {
 struct WideRay {
     f3 o, d;
     f3 idir;        // 1 / d with |d| clamped away from 0
+    f3 pad_scale;   // |idir| * 2^-21: conservative slack per unit of coordinate magnitude
     uint32_t oct_inv4;  // (dx>=0 ? 4 : 0 | dy>=0 ? 2 : 0 | dz>=0 ? 1 : 0) * 0x01010101
 };
 
@@ -78,6 +79,7 @@ RPT_D WideRay make_wide_ray(f3 o, f3 d) {
     r.o = o;
     r.d = d;
     r.idir = mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+    r.pad_scale = mk3(fabsf(r.idir.x) * 4.8e-7f, fabsf(r.idir.y) * 4.8e-7f, fabsf(r.idir.z) * 4.8e-7f);
     const uint32_t oct = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
     r.oct_inv4 = oct * 0x01010101u;
     return r;
@@ -158,12 +160,12 @@ struct WideCursor {
         const f3 p = mk3(as_float(n0.x), as_float(n0.y), as_float(n0.z));
         const f3 cell = mk3(as_float((n0.w & 0xFFu) << 23), as_float(((n0.w >> 8) & 0xFFu) << 23), as_float(((n0.w >> 16) & 0xFFu) << 23));
         const f3 adj = cell * ray.idir;
-        // push the planes out by a few ulps of the coordinates involved, so that rounding in
-        // (p - o) * idir can never cull a box the exact arithmetic would enter
-        const f3 pad = mk3((fabsf(p.x) + fabsf(ray.o.x) + 256.0f * cell.x) * 4.8e-7f, (fabsf(p.y) + fabsf(ray.o.y) + 256.0f * cell.y) * 4.8e-7f,
-                           (fabsf(p.z) + fabsf(ray.o.z) + 256.0f * cell.z) * 4.8e-7f);
+        // Push the planes out by a few ulps so rounding can never cull a box the exact arithmetic
+        // would enter: p - o, its product with idir and the FMA below are each correctly rounded,
+        // i.e. off by < 2^-23 of |p - o| resp. of the box extent (<= 256 cells); pad by 2^-21 of both.
         const f3 rel_o = p - ray.o;
-        const f3 apad = mk3(fabsf(ray.idir.x) * pad.x, fabsf(ray.idir.y) * pad.y, fabsf(ray.idir.z) * pad.z);
+        const f3 apad = mk3(fmaf(256.0f, cell.x, fabsf(rel_o.x)) * ray.pad_scale.x, fmaf(256.0f, cell.y, fabsf(rel_o.y)) * ray.pad_scale.y,
+                            fmaf(256.0f, cell.z, fabsf(rel_o.z)) * ray.pad_scale.z);
         const f3 org = rel_o * ray.idir;
         const f3 org_near = org - apad, org_far = org + apad;
 

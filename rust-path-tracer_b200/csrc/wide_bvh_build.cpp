@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 
@@ -43,7 +44,45 @@ class Collapser {
               uint32_t nverts, WideBvh& out)
         : nodes_(nodes), nnodes_(nnodes), tris_(tris), ntris_(ntris), verts_(verts), nverts_(nverts), out_(out) {}
 
+    // Triangle range covered by every binary subtree (the reference builder partitions the index
+    // buffer in place, so a subtree owns one contiguous run); count 0 marks "not contiguous".
+    bool subtree_ranges() {
+        sub_first_.assign(nnodes_, 0u);
+        sub_count_.assign(nnodes_, 0u);
+        std::vector<uint32_t> order, todo{0u};
+        order.reserve(nnodes_);
+        std::vector<uint8_t> seen(nnodes_, 0);
+        while (!todo.empty()) {
+            const uint32_t ni = todo.back();
+            todo.pop_back();
+            if (ni >= nnodes_ || seen[ni]) return false;
+            seen[ni] = 1;
+            order.push_back(ni);
+            if (nodes_[ni].triangle_count == 0) {
+                if ((uint64_t)nodes_[ni].left_or_first + 1 >= nnodes_) return false;
+                todo.push_back(nodes_[ni].left_or_first);
+                todo.push_back(nodes_[ni].left_or_first + 1);
+            }
+        }
+        for (size_t k = order.size(); k-- > 0;) {  // children appear after their parent in `order`
+            const uint32_t ni = order[k];
+            const RptBVHNode& n = nodes_[ni];
+            if (n.triangle_count > 0) {
+                sub_first_[ni] = n.left_or_first;
+                sub_count_[ni] = n.triangle_count;
+            } else {
+                const uint32_t l = n.left_or_first, r = l + 1;
+                if (sub_count_[l] && sub_count_[r] && sub_first_[l] + sub_count_[l] == sub_first_[r]) {
+                    sub_first_[ni] = sub_first_[l];
+                    sub_count_[ni] = sub_count_[l] + sub_count_[r];
+                }
+            }
+        }
+        return true;
+    }
+
     bool run(const char** error) {
+        if (!subtree_ranges()) { *error = "malformed BVH: child index out of range or node referenced twice"; return false; }
         out_.nodes.clear();
         out_.tri_pos.clear();
         out_.orig_index.clear();
@@ -132,6 +171,13 @@ class Collapser {
             it.is_range = true;
             it.first = n.left_or_first;
             it.count = n.triangle_count;
+        } else if (sub_count_[ni] != 0 && sub_count_[ni] <= leaf_merge_) {
+            // a whole binary subtree of at most three triangles becomes ONE leaf slot: fewer wide nodes
+            // to visit at the price of testing its triangles together
+            if ((uint64_t)sub_first_[ni] + sub_count_[ni] > ntris_) return false;
+            it.is_range = true;
+            it.first = sub_first_[ni];
+            it.count = sub_count_[ni];
         } else {
             if ((uint64_t)n.left_or_first + 1 >= nnodes_) return false;
             it.is_range = false;
@@ -252,6 +298,10 @@ class Collapser {
     const RptPerVertexData* verts_;
     uint32_t nverts_;
     WideBvh& out_;
+    std::vector<uint32_t> sub_first_, sub_count_;
+
+  public:
+    uint32_t leaf_merge_ = 1;  // largest binary subtree (in triangles) folded into one leaf slot; 1 = off
 };
 
 }  // namespace
@@ -268,6 +318,7 @@ bool build_wide_bvh(const RptBVHNode* nodes, uint32_t nnodes, const uint32_t* tr
             if (triangles[4 * t + k] >= nvertices) { *error = "triangle references a vertex out of range"; return false; }
     out = WideBvh{};
     Collapser c(nodes, nnodes, triangles, ntriangles, vertices, nvertices, out);
+    if (const char* v = std::getenv("RPT_LEAF_MERGE")) c.leaf_merge_ = (uint32_t)std::min(3, std::max(1, std::atoi(v)));
     return c.run(error);
 }
 
