@@ -195,11 +195,9 @@ def run_b200(args):
     seeds[:, 0] += np.uint32(rank * (args.steps + args.warmup) * spp)
     r.write_rng(seeds)
     if dist is not None:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(Renderer.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        r.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world_size)
+        from rust_path_tracer_b200.dist import init_comm
+
+        init_comm(r, dist, rank, world_size)
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps --------------
     for _ in range(args.warmup):

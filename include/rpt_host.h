@@ -8,6 +8,7 @@
  *                                  src/light_pick.rs:13-122 (called from src/asset.rs:201-202)
  *   rpt_pack_per_vertex         <- the PerVertexData packing loop, src/asset.rs:205-215
  *   rpt_make_rng_seeds          <- blue-noise / uniform seed tables, src/trace.rs:149-160, 245-256
+ *   rpt_tile_partition_pixels   <- (new) the tile split used by rpt_set_tile_partition
  *   rpt_camera_matrix           <- Mat3::from_rotation_y(ry) * Mat3::from_rotation_x(rx),
  *                                  kernels/src/lib.rs:50 (host libm keeps primary rays bit-exact)
  *
@@ -44,6 +45,11 @@ int rpt_pack_per_vertex(const float* vertices, const float* normals, const float
  * (blue-noise mode); blue == NULL: x = splitmix-style uniform from `uniform_seed`, y = 0. */
 int rpt_make_rng_seeds(const uint8_t* blue_r8, uint32_t bw, uint32_t bh, uint32_t width, uint32_t height,
                        uint64_t uniform_seed, uint32_t* seeds_xy_out);
+
+/* Multi-GPU tile split: pixel indices (row-major y*width+x) of the 32x32 tiles t
+ * with t % tile_count == tile_rank, tile by tile.  pixels_out may be NULL to query the count. */
+int rpt_tile_partition_pixels(uint32_t width, uint32_t height, uint32_t tile_rank, uint32_t tile_count,
+                              uint32_t* pixels_out, uint32_t* npixels_out);
 
 /* 3x3 camera rotation, column-major (col0,col1,col2), computed with the host libm. */
 int rpt_camera_matrix(float rot_x, float rot_y, float* m9_out);

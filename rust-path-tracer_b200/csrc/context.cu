@@ -285,15 +285,10 @@ int rebuild_pixel_map(rpt_context* c) {
     c->d_pixel_map.release();
     c->pixel_map_len = 0;
     if (c->tile_count <= 1 || !c->has_config) return RPT_OK;
-    const uint32_t W = c->config.width, H = c->config.height, tiles_x = (W + 31u) / 32u;
-    std::vector<uint32_t> map;
-    map.reserve((size_t)W * H / c->tile_count + 1024);
-    for (uint32_t ty = 0; ty * 32u < H; ++ty)
-        for (uint32_t tx = 0; tx < tiles_x; ++tx) {
-            if ((ty * tiles_x + tx) % c->tile_count != c->tile_rank) continue;
-            for (uint32_t y = ty * 32u; y < std::min(H, ty * 32u + 32u); ++y)
-                for (uint32_t x = tx * 32u; x < std::min(W, tx * 32u + 32u); ++x) map.push_back(y * W + x);
-        }
+    uint32_t count = 0;
+    rpt_tile_partition_pixels(c->config.width, c->config.height, c->tile_rank, c->tile_count, nullptr, &count);
+    std::vector<uint32_t> map(count);
+    if (count) rpt_tile_partition_pixels(c->config.width, c->config.height, c->tile_rank, c->tile_count, map.data(), &count);
     c->pixel_map_len = (uint32_t)map.size();
     if (!map.empty()) {
         RPT_CUDA(c, c->d_pixel_map.upload(map.data(), map.size(), c->stream));

@@ -328,6 +328,24 @@ extern "C" int rpt_make_rng_seeds(const uint8_t* blue_r8, uint32_t bw, uint32_t 
     return RPT_OK;
 }
 
+extern "C" int rpt_tile_partition_pixels(uint32_t width, uint32_t height, uint32_t tile_rank, uint32_t tile_count,
+                                         uint32_t* pixels_out, uint32_t* npixels_out) {
+    if (!npixels_out || tile_count == 0 || tile_rank >= tile_count || width == 0 || height == 0) return RPT_ERR_INVALID_ARGUMENT;
+    const uint32_t tiles_x = (width + 31u) / 32u;
+    uint32_t n = 0;
+    for (uint32_t ty = 0; ty * 32u < height; ++ty)
+        for (uint32_t tx = 0; tx < tiles_x; ++tx) {
+            if ((ty * tiles_x + tx) % tile_count != tile_rank) continue;
+            for (uint32_t y = ty * 32u; y < std::min(height, ty * 32u + 32u); ++y)
+                for (uint32_t x = tx * 32u; x < std::min(width, tx * 32u + 32u); ++x) {
+                    if (pixels_out) pixels_out[n] = y * width + x;
+                    ++n;
+                }
+        }
+    *npixels_out = n;
+    return RPT_OK;
+}
+
 extern "C" int rpt_camera_matrix(float rot_x, float rot_y, float* m) {
     if (!m) return RPT_ERR_INVALID_ARGUMENT;
     // glam: from_rotation_y cols (c,0,-s),(0,1,0),(s,0,c); from_rotation_x cols (1,0,0),(0,c,s),(0,-s,c)
