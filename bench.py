@@ -41,6 +41,11 @@ WORKLOADS = {
     "furnace": ("FurnaceTest", 256, 256, 0, 16, "configs[0] FurnaceTest.glb 256x256"),
     "pbr": ("PBRTest", 1920, 1080, 0, 16, "configs[2] PBRTest.glb 1920x1080, procedural sky"),
     "veach": ("VeachMIS", 1920, 1080, 1, 32, "configs[3] VeachMIS.glb 1920x1080, MIS"),
+    # synthetic inputs (rust-path-tracer_b200/scenes.py): the shipped assets have no textures, and
+    # scenes/BreakTime.glb is absent from the reference checkout (.MISSING_LARGE_BLOBS)
+    "pbr-textured": ("PBRTest+procedural textures", 1920, 1080, 0, 16, "configs[2] PBRTest.glb 1920x1080 with a synthetic 4096^2 metallic/roughness/albedo/normal atlas"),
+    "breaktime": ("BreakTime PROXY (synthetic ~1M-triangle textured interior, HDR sky)", 1920, 1080, 1, 16,
+                  "north-star scene BreakTime.glb 1920x1080 — asset absent, LABELLED SYNTHETIC PROXY"),
 }
 
 
@@ -104,20 +109,36 @@ def load_workload(name):
     from rust_path_tracer_b200.world import World, make_rng_seeds
 
     scene, w, h, nee, spp, label = WORKLOADS[name]
-    world = World.from_path(os.path.join(REPO, "tests", "golden", "scenes", scene + ".npz"))
-    if world is None:
-        raise SystemExit(f"cannot load scene fixture for {scene}")
     cfg = TracingConfig.default(w, h)
     cfg.nee = nee
-    return world, cfg, make_rng_seeds(w, h), spp, label, scene
+    sky = None
+    if name == "pbr-textured":
+        from rust_path_tracer_b200.glb import BakedScene
+        from rust_path_tracer_b200.scenes import textured_pbr_variant
+
+        baked, atlas = textured_pbr_variant(BakedScene.load(os.path.join(REPO, "tests", "golden", "scenes", "PBRTest.npz")))
+        world = World.from_baked(baked, atlas=atlas)
+    elif name == "breaktime":
+        from rust_path_tracer_b200.scenes import breaktime_proxy, synthetic_hdr_sky
+
+        baked, atlas = breaktime_proxy()
+        world = World.from_baked(baked, atlas=atlas)
+        sky = synthetic_hdr_sky()
+        cfg.has_skybox = 1
+    else:
+        world = World.from_path(os.path.join(REPO, "tests", "golden", "scenes", scene + ".npz"))
+        scene += " (fixture of the shipped .glb)"
+    if world is None:
+        raise SystemExit(f"cannot load scene fixture for {scene}")
+    return world, cfg, make_rng_seeds(w, h), spp, label, scene, sky
 
 
-def oracle_sample(world, cfg, seeds, spp, threads=0):
+def oracle_sample(world, cfg, seeds, spp, threads=0, sky=None):
     """Time the CPU oracle on `spp` samples of the workload; returns (seconds, counters)."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import oracle as oracle_mod
 
-    scene = oracle_mod.OracleScene(world)
+    scene = oracle_mod.OracleScene(world, sky)
     t0 = time.perf_counter()
     _, _, ctr, _ = oracle_mod.trace(cfg, scene, seeds, spp, threads=threads)
     return time.perf_counter() - t0, ctr, oracle_mod.max_threads() if threads == 0 else threads
@@ -131,13 +152,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    world, cfg, seeds, _spp, label, scene = load_workload(args.workload)
+    world, cfg, seeds, _spp, label, scene, sky = load_workload(args.workload)
     ref_spp = 1
     for _ in range(args.warmup):
-        oracle_sample(world, cfg, seeds, ref_spp)
+        oracle_sample(world, cfg, seeds, ref_spp, sky=sky)
     times, rays = [], 0
     for _ in range(args.steps):
-        dt, ctr, threads = oracle_sample(world, cfg, seeds, ref_spp)
+        dt, ctr, threads = oracle_sample(world, cfg, seeds, ref_spp, sky=sky)
         times.append(dt)
         rays += ctr["nearest_rays"] + ctr["any_rays"]
     total = sum(times)
@@ -147,7 +168,7 @@ def run_reference(args):
         "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": label, "scene": scene + " (fixture of the shipped .glb)", "width": cfg.width, "height": cfg.height,
+        "config": {"workload": label, "scene": scene, "width": cfg.width, "height": cfg.height,
                    "nee": cfg.nee, "spp_per_step": ref_spp},
         "mrays_per_s": rays / total / 1e6,
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": threads, "kind": "port",
@@ -180,13 +201,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    world, cfg, seeds0, spp, label, scene = load_workload(args.workload)
+    world, cfg, seeds0, spp, label, scene, sky = load_workload(args.workload)
     if args.spp:
         spp = args.spp
     npix = cfg.width * cfg.height
     pipeline = capi.PIPELINE_MEGAKERNEL if args.pipeline == "megakernel" else capi.PIPELINE_WAVEFRONT
     r = Renderer(local_rank, pipeline)
-    r.upload_world(world)
+    r.upload_world(world, sky)
     r.set_config(cfg)
     if args.wave_slots:
         r.set_wave_slots(args.wave_slots)
@@ -202,6 +223,8 @@ def run_b200(args):
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps --------------
     for _ in range(args.warmup):
         r.enqueue(spp)
+    if dist is not None:
+        r.comm_reduce_output(0)  # the first collective builds NCCL's channels: keep that out of the timed region
     r.sync()
     r.write_output(None)
     r.reset_counters()
@@ -233,7 +256,7 @@ def run_b200(args):
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * job_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": label, "scene": scene + " (fixture of the shipped .glb)", "width": cfg.width, "height": cfg.height,
+        "config": {"workload": label, "scene": scene, "width": cfg.width, "height": cfg.height,
                    "nee": cfg.nee, "min_bounces": cfg.min_bounces, "max_bounces": cfg.max_bounces, "spp_per_step": spp,
                    "pipeline": args.pipeline, "partition": f"sample-index range x{world_size} + ncclReduce" if world_size > 1 else "single GPU",
                    "l2": "working set per step (path state %.0f MB) exceeds the 126 MB L2" % (152.0 * min(npix * spp, args.wave_slots or (1 << 22)) / 1e6)},
@@ -254,7 +277,7 @@ def run_b200(args):
         ext_ms, ext_launches = stages["extend"] if pipeline == capi.PIPELINE_WAVEFRONT else stages["megakernel"]
         # algorithmic bytes per nearest ray, in the reference's layout: 32 B per box slab-tested + 64 B per
         # triangle tested (16 B index + 3 x 16 B positions) — SURVEY.md §8(d); counted by the oracle on 1 spp
-        dt1, octr, threads = oracle_sample(world, cfg, seeds0, 1)
+        dt1, octr, threads = oracle_sample(world, cfg, seeds0, 1, sky=sky)
         boxes_n = octr["boxes_tested"] - octr["boxes_tested_any"]
         tris_n = octr["tris_tested"] - octr["tris_tested_any"]
         bytes_per_ray = (32.0 * boxes_n + 64.0 * tris_n) / max(octr["nearest_rays"], 1)
@@ -275,7 +298,7 @@ def run_b200(args):
         }
         # ---- CPU baseline: the oracle port on the host cores, bounded sample ------------------
         cpu_spp = max(1, min(8, int(15.0 / max(dt1, 1e-3))))
-        dtc, cctr, threads = oracle_sample(world, cfg, seeds0, cpu_spp)
+        dtc, cctr, threads = oracle_sample(world, cfg, seeds0, cpu_spp, sky=sky)
         line["cpu_baseline"] = {"value": npix * cpu_spp / dtc / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "port",
                                 "mrays_per_s": (cctr["nearest_rays"] + cctr["any_rays"]) / dtc / 1e6,
                                 "sample": f"{cpu_spp} spp of the full {cfg.width}x{cfg.height} frame ({dtc:.1f} s), OpenMP rows"}

@@ -61,3 +61,25 @@ def synthetic_sky(width: int = 64, height: int = 32, seed: int = 7) -> np.ndarra
     img[height // 4 : height // 4 + 3, width // 3 : width // 3 + 3, :3] = 40.0
     img[..., 3] = 1.0
     return img
+
+
+@functools.lru_cache(maxsize=None)
+def textured_world(texture_size: int = 64, atlas_size: int = 1024):
+    """PBRTest with procedural albedo / metallic / roughness / normal textures on its 25 sphere materials
+    (the shipped scenes contain no image)."""
+    from rust_path_tracer_b200.glb import BakedScene
+    from rust_path_tracer_b200.scenes import textured_pbr_variant
+    from rust_path_tracer_b200.world import World
+
+    scene, atlas = textured_pbr_variant(BakedScene.load(os.path.join(SCENE_DIR, "PBRTest.npz")), texture_size, atlas_size)
+    return World.from_baked(scene, atlas=atlas)
+
+
+@functools.lru_cache(maxsize=None)
+def proxy_world(triangles: int = 60000):
+    """Small instance of the labelled BreakTime proxy (textured, emitters, windows)."""
+    from rust_path_tracer_b200.scenes import breaktime_proxy
+    from rust_path_tracer_b200.world import World
+
+    scene, atlas = breaktime_proxy(triangles, texture_size=64, atlas_size=512)
+    return World.from_baked(scene, atlas=atlas)

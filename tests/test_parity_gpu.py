@@ -120,6 +120,33 @@ def test_hdr_sky_and_rotated_camera():
         assert err <= MAE_TOLERANCE, err
 
 
+@pytest.mark.parametrize("pipeline", [capi.PIPELINE_WAVEFRONT, capi.PIPELINE_MEGAKERNEL], ids=["wavefront", "megakernel"])
+def test_textured_atlas_and_normal_maps(pipeline):
+    """Config 3's "textured metallic/roughness atlas": procedural albedo / metallic / roughness / normal
+    textures on PBRTest (no shipped scene has images) — exercises the bilinear polyfill fetch and TBN."""
+    world = helpers.textured_world()
+    cfg = helpers.config(160, 88, 0)
+    seeds = helpers.seeds(160, 88)
+    o_out, _, o_ids, _ = render_oracle(world, cfg, seeds, 16)
+    c_out, _, c_ids, _ = render_cuda(world, cfg, seeds, 16, pipeline)
+    assert float((c_ids != o_ids).mean()) <= ID_MISMATCH_BUDGET
+    err, _ = helpers.mae(c_out[:, :3] / 16, o_out[:, :3] / 16)
+    assert err <= MAE_TOLERANCE, err
+
+
+def test_breaktime_proxy_scene():
+    """Labelled stand-in for the absent BreakTime.glb: textured interior, emitters, HDR sky through windows."""
+    world = helpers.proxy_world()
+    sky = helpers.synthetic_sky(128, 64)
+    cfg = helpers.config(160, 90, 1, has_skybox=1)
+    seeds = helpers.seeds(160, 90)
+    o_out, _, o_ids, _ = render_oracle(world, cfg, seeds, 16, sky)
+    c_out, _, c_ids, _ = render_cuda(world, cfg, seeds, 16, capi.PIPELINE_WAVEFRONT, sky)
+    assert float((c_ids != o_ids).mean()) <= ID_MISMATCH_BUDGET
+    err, bad = helpers.mae(c_out[:, :3] / 16, o_out[:, :3] / 16)
+    assert err <= MAE_TOLERANCE, err
+
+
 @pytest.mark.parametrize("use_mis", [False, True])
 def test_furnace_known_answer(use_mis):
     """tests/correctness_tests.rs:14-33 through the mirrored harness: 128x128, 32 spp, pixel (65,75)."""

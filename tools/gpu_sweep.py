@@ -8,13 +8,13 @@ import bench
 from rust_path_tracer_b200.trace import Renderer
 
 workload, spp = sys.argv[1], int(sys.argv[2])
-world, cfg, seeds, _, label, scene = bench.load_workload(workload)
+world, cfg, seeds, _, label, scene, sky = bench.load_workload(workload)
 for setting in sys.argv[3:] or [""]:
     for kv in filter(None, setting.split(",")):
         k, v = kv.split("=")
         os.environ[k] = v
     with Renderer(0) as r:
-        r.upload_world(world); r.set_config(cfg); r.write_rng(seeds)
+        r.upload_world(world, sky); r.set_config(cfg); r.write_rng(seeds)
         r.enqueue(spp); r.sync()
         r.reset_counters(); r.enqueue(spp); ms = r.device_ms(); c = r.counters()
         r.set_stage_timing(True); r.enqueue(spp); st = r.stage_timing()
