@@ -319,6 +319,7 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
         const int cur = (int)(b & 1u), nxt = cur ^ 1;
         if (b > 0) c->launch(RPT_STAGE_OTHER, [&] { launch_wf_reset(l, s, nxt, false); });
         c->launch(RPT_STAGE_EXTEND, [&] { launch_wf_extend(l, w.bvh, s, cur, b == 0, nslots); });
+        c->kernel_launches++;  // extend = trace + queue compaction
         if (primary_only) {
             c->launch(RPT_STAGE_OTHER, [&] { launch_wf_export_primary(l, w.bvh, s, d, ids_out); });
             c->kernel_launches++;  // the export is two kernels

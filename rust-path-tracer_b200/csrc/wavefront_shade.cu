@@ -13,31 +13,23 @@
 
 namespace rpt {
 
-constexpr int kShadeBlock = 128;
+constexpr int kShadeBlock = 256;
+constexpr int kShadeWarps = kShadeBlock / 32;
 constexpr uint32_t kSmemMaterials = 64;    // 6 KB
 constexpr uint32_t kSmemLightBins = 1024;  // 12 KB
-
-__device__ __forceinline__ uint32_t warp_reserve(bool pred, uint32_t* count, uint32_t& rank_out) {
-    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
-    if (mask == 0u) return 0u;
-    const uint32_t lane = threadIdx.x & 31u;
-    const int leader = __ffs((int)mask) - 1;
-    uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    rank_out = (uint32_t)__popc(mask & ((1u << lane) - 1u));
-    return base;
-}
 
 __device__ __forceinline__ uint32_t wave_pixel(const WaveDesc& d, uint32_t j) {
     const uint32_t i = d.pix_base + j;
     return d.pixel_map ? __ldg(d.pixel_map + i) : i;
 }
 
-__global__ void __launch_bounds__(kShadeBlock) wf_shade_kernel(FrameParams f, WideWorld w, WaveState s, WaveDesc d, const uint2* __restrict__ rng,
+__global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f, WideWorld w, WaveState s, WaveDesc d, const uint2* __restrict__ rng,
                                                                uint32_t bounce, int out_queue) {
     __shared__ RptMaterialData sm_materials[kSmemMaterials];
     __shared__ LightBin sm_bins[kSmemLightBins];
+    // queue appends are aggregated per block: warp ballots -> these counters -> one atomic pair per block
+    // and iteration (a single device counter sustains only a few atomics per nanosecond)
+    __shared__ uint32_t warp_shadow[kShadeWarps], warp_next[kShadeWarps], block_base[2];
     const bool mats_in_smem = w.nmaterials <= kSmemMaterials;
     const bool bins_in_smem = w.nbins > 0 && w.nbins <= kSmemLightBins;
     if (mats_in_smem) {
@@ -55,10 +47,10 @@ __global__ void __launch_bounds__(kShadeBlock) wf_shade_kernel(FrameParams f, Wi
     const uint32_t n = s.ctl->n_hit;
     const bool nee = f.nee != RPT_NEE_NONE;
     const bool last_bounce = bounce + 1u >= f.max_bounces;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
-        const uint32_t i = base + lane;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {  // block-uniform trip count
+        const uint32_t i = base + threadIdx.x;
         bool want_shadow = false, want_next = false;
         uint32_t slot = 0;
         f3 sh_o{}, sh_d{}, sh_c{};
@@ -196,25 +188,35 @@ __global__ void __launch_bounds__(kShadeBlock) wf_shade_kernel(FrameParams f, Wi
                 }
             }
         }
-        __syncwarp();
-        uint32_t rank = 0;
-        uint32_t qb = warp_reserve(want_shadow, &s.ctl->n_shadow, rank);
-        if (want_shadow) {
-            s.sh_o[qb + rank] = mk4(sh_o, sh_tmax);
-            s.sh_d[qb + rank] = mk4(sh_d, __uint_as_float(slot));
-            s.sh_c[qb + rank] = mk4(sh_c, 0.0f);
+        const uint32_t sh_mask = __ballot_sync(0xFFFFFFFFu, want_shadow), nx_mask = __ballot_sync(0xFFFFFFFFu, want_next);
+        if (lane == 0) { warp_shadow[warp] = (uint32_t)__popc(sh_mask); warp_next[warp] = (uint32_t)__popc(nx_mask); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t ts = 0, tn = 0;
+            for (int w = 0; w < kShadeWarps; ++w) { const uint32_t a = warp_shadow[w], b = warp_next[w]; warp_shadow[w] = ts; warp_next[w] = tn; ts += a; tn += b; }
+            block_base[0] = ts ? atomicAdd(&s.ctl->n_shadow, ts) : 0u;
+            block_base[1] = tn ? atomicAdd(out_queue ? &s.ctl->n_ext[1] : &s.ctl->n_ext[0], tn) : 0u;
         }
-        qb = warp_reserve(want_next, out_queue ? &s.ctl->n_ext[1] : &s.ctl->n_ext[0], rank);
+        __syncthreads();
+        const uint32_t below = (1u << lane) - 1u;
+        if (want_shadow) {
+            const uint32_t q = block_base[0] + warp_shadow[warp] + (uint32_t)__popc(sh_mask & below);
+            s.sh_o[q] = mk4(sh_o, sh_tmax);
+            s.sh_d[q] = mk4(sh_d, __uint_as_float(slot));
+            s.sh_c[q] = mk4(sh_c, 0.0f);
+        }
         if (want_next) {
-            (out_queue ? s.q_ext[1] : s.q_ext[0])[qb + rank] = slot;
+            const uint32_t q = block_base[1] + warp_next[warp] + (uint32_t)__popc(nx_mask & below);
+            (out_queue ? s.q_ext[1] : s.q_ext[0])[q] = slot;
             s.ray_o[slot] = mk4(next_o, 0.0f);
             s.ray_d[slot] = mk4(next_d, __uint_as_float(next_flags));
             s.thr[slot] = mk4(next_thr, next_pdf);
         }
+        __syncthreads();  // the shared counters are rewritten next iteration
     }
 }
 
-__global__ void __launch_bounds__(kShadeBlock) wf_miss_kernel(FrameParams f, WaveState s) {
+__global__ void __launch_bounds__(128) wf_miss_kernel(FrameParams f, WaveState s) {
     const uint32_t n = s.ctl->n_miss;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t slot = __ldg(s.q_miss + i);
@@ -264,11 +266,11 @@ __global__ void normalize_kernel(const float4* __restrict__ output, float* __res
 
 void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld& w, const WaveState& s, const WaveDesc& d, const uint2* rng,
                      uint32_t bounce, int out_queue) {
-    wf_shade_kernel<<<l.grid * 6, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce, out_queue);
+    wf_shade_kernel<<<l.grid * 4, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce, out_queue);
 }
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole) { wf_reset_kernel<<<1, 32, 0, l.stream>>>(s, next_queue, whole); }
 void launch_wf_miss(const WaveLaunch& l, const FrameParams& f, const WaveState& s) {
-    wf_miss_kernel<<<l.grid * 8, kShadeBlock, 0, l.stream>>>(f, s);
+    wf_miss_kernel<<<l.grid * 8, 128, 0, l.stream>>>(f, s);
 }
 void launch_wf_accumulate(const WaveLaunch& l, const WaveState& s, const WaveDesc& d, uint2* rng, float4* output) {
     wf_accumulate_kernel<<<l.grid * 2, 256, 0, l.stream>>>(s, d, rng, output);

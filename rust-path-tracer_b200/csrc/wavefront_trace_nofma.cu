@@ -64,7 +64,9 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(FrameParams f, WaveSta
 
 // Persistent trace kernel for both ray kinds.
 //   NEAREST: items are path slots (queue q_ext[in_queue], or 0..n_identity-1 for bounce 0); the hit
-//            record goes to s.hit[slot] and the slot is appended to q_hit or q_miss.
+//            (or miss) record goes to s.hit[slot]; wf_compact_kernel then splits the slots into
+//            q_hit / q_miss IN QUEUE ORDER, so the shading stages read path state coalesced
+//            although rays finish in any order here.
 //   ANY:     items are shadow-queue entries; an unoccluded ray adds its contribution to rad[slot].
 // Lanes pull rays one at a time from a device-side cursor: when a lane's ray terminates it waits
 // only until the warp's live-lane count drops below `refill_below`, then every idle lane is handed
@@ -72,6 +74,8 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(FrameParams f, WaveSta
 // Inside the traversal loop a lane that reaches triangles while fewer than `postpone_frac` of the
 // live lanes have any pushes the triangle group back on its stack and goes on with nodes first
 // (triangle postponing), so ray/triangle tests execute with more lanes enabled.
+
+constexpr uint32_t kMissRecord = 0xFFFFFFFFu;  // hit[].y of a ray that hit nothing (triangle indices are < 2^31)
 
 template <bool NEAREST>
 __global__ void __launch_bounds__(kTraceBlock) wf_trace_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
@@ -88,16 +92,10 @@ __global__ void __launch_bounds__(kTraceBlock) wf_trace_kernel(WideScene bvh, Wa
     WideCursor<NEAREST> c;
     uint32_t item = 0;       // path slot (NEAREST) / shadow-queue index (ANY)
     bool busy = false;       // this lane holds an unfinished ray
-    bool publish = false;    // NEAREST: a finished ray waits for the warp-wide queue append
     bool exhausted = false;  // the cursor ran past the end of the queue (warp-uniform)
 
     for (;;) {
-        // ---- converged: publish finished rays, then refill idle lanes ------------------------
-        if (NEAREST) {
-            warp_append(publish && c.res.hit, s.q_hit, &s.ctl->n_hit, item);
-            warp_append(publish && !c.res.hit, s.q_miss, &s.ctl->n_miss, item);
-            publish = false;
-        }
+        // ---- converged: refill idle lanes -------------------------------------------------------
         if (!exhausted) {
             const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !busy);
             if (idle) {
@@ -148,9 +146,9 @@ __global__ void __launch_bounds__(kTraceBlock) wf_trace_kernel(WideScene bvh, Wa
             if (!finished && !c.advance(st)) finished = true;
             if (finished) {
                 busy = false;
-                if (NEAREST) {
-                    if (c.res.hit) s.hit[item] = make_uint2(__float_as_uint(c.res.t), c.res.triangle | (c.res.backface ? 0x80000000u : 0u));
-                    publish = true;
+                if (NEAREST) {  // every traced slot gets a record; kMissRecord marks "no hit" for wf_compact_kernel
+                    s.hit[item] = c.res.hit ? make_uint2(__float_as_uint(c.res.t), c.res.triangle | (c.res.backface ? 0x80000000u : 0u))
+                                            : make_uint2(0u, kMissRecord);
                 } else if (!c.res.hit) {  // unoccluded: radiance += mask_nan(contribution) (lib.rs:164; masked when queued)
                     const uint32_t slot = __float_as_uint(s.sh_d[item].w);
                     const float4 add = s.sh_c[item];
@@ -162,6 +160,41 @@ __global__ void __launch_bounds__(kTraceBlock) wf_trace_kernel(WideScene bvh, Wa
             }
             if (!exhausted && __popc(__activemask()) < refill_below) break;
         }
+    }
+}
+
+// Ballot/popc stream compaction of the traced slots into the hit and miss queues, in input order.
+// Counts are aggregated per block (warp ballots -> shared memory -> ONE atomic pair per block and
+// iteration), because a single counter only sustains a few atomics per nanosecond.
+__global__ void __launch_bounds__(256) wf_compact_kernel(WaveState s, int in_queue, bool identity, uint32_t n_identity) {
+    __shared__ uint32_t warp_hits[8], warp_misses[8], block_base[2];
+    const uint32_t n = identity ? n_identity : (in_queue ? s.ctl->n_ext[1] : s.ctl->n_ext[0]);
+    const uint32_t* __restrict__ queue = in_queue ? s.q_ext[1] : s.q_ext[0];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {  // block-uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        const bool active = i < n;
+        uint32_t slot = 0;
+        bool hit = false;
+        if (active) {
+            slot = identity ? i : __ldg(queue + i);
+            hit = s.hit[slot].y != kMissRecord;
+        }
+        const uint32_t hmask = __ballot_sync(0xFFFFFFFFu, active && hit), mmask = __ballot_sync(0xFFFFFFFFu, active && !hit);
+        if (lane == 0) { warp_hits[warp] = (uint32_t)__popc(hmask); warp_misses[warp] = (uint32_t)__popc(mmask); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t th = 0, tm = 0;
+            for (int w = 0; w < 8; ++w) { const uint32_t h = warp_hits[w], m = warp_misses[w]; warp_hits[w] = th; warp_misses[w] = tm; th += h; tm += m; }
+            block_base[0] = th ? atomicAdd(&s.ctl->n_hit, th) : 0u;
+            block_base[1] = tm ? atomicAdd(&s.ctl->n_miss, tm) : 0u;
+        }
+        __syncthreads();
+        const uint32_t below = (1u << lane) - 1u;
+        if (active && hit) s.q_hit[block_base[0] + warp_hits[warp] + (uint32_t)__popc(hmask & below)] = slot;
+        if (active && !hit) s.q_miss[block_base[1] + warp_misses[warp] + (uint32_t)__popc(mmask & below)] = slot;
+        __syncthreads();  // block_base / warp_* are rewritten next iteration
     }
 }
 
@@ -185,6 +218,7 @@ void launch_wf_generate(const WaveLaunch& l, const FrameParams& f, const WaveSta
 }
 void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, int in_queue, bool identity_queue, uint32_t n_identity) {
     wf_trace_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.postpone_frac);
+    wf_compact_kernel<<<l.grid * 4, 256, 0, l.stream>>>(s, in_queue, identity_queue, n_identity);
 }
 void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState& s) {
     wf_trace_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.postpone_frac);
