@@ -294,7 +294,7 @@ def run_b200(args):
             bytes_any = (32.0 * octr["boxes_tested_any"] + 64.0 * octr["tris_tested_any"]) / max(octr["any_rays"], 1)
             achieved = (c1["nearest_rays"] * bytes_per_ray + c1["any_rays"] * bytes_any) / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
         line["roofline"] = {
-            "bound": "hbm", "kernel": "wf_extend_kernel" if pipeline == capi.PIPELINE_WAVEFRONT else "mega_trace_kernel",
+            "bound": "hbm", "kernel": "wf_trace_kernel<true> (extend)" if pipeline == capi.PIPELINE_WAVEFRONT else "mega_trace_kernel",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "peak_source": peak_src, "algorithmic_bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch,
             "ms_per_launch": ms_per_launch, "launches_timed": ext_launches,

@@ -93,6 +93,25 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_host_tools() -> dict:
+    """The C++ host mirror of src/trace.rs (host/) with its test and bench executables, linked against the library."""
+    hdir = os.path.join(PKG_DIR, "host")
+    build_library()
+    out = {}
+    common = [os.path.join(hdir, "trace.cpp")]
+    for name in ("correctness_tests", "benchmark"):
+        exe = os.path.join(OUT_DIR, name)
+        srcs = common + [os.path.join(hdir, name + ".cpp")]
+        if _stale(exe, srcs + [os.path.join(hdir, "trace.hpp"), LIB_PATH]):
+            cmd = [HOST_CXX, "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", *srcs, "-o", exe, "-L", OUT_DIR, "-lrpt_b200",
+                   "-Wl,-rpath," + OUT_DIR]
+            p = subprocess.run(cmd, capture_output=True, text=True)
+            if p.returncode != 0:
+                raise RuntimeError(f"host tool build failed:\n{p.stdout}\n{p.stderr}")
+        out[name] = exe
+    return out
+
+
 def build_oracle() -> str:
     """Build the CPU oracle (test infrastructure) through its own Makefile."""
     odir = os.path.join(REPO_DIR, "oracle")

@@ -73,6 +73,18 @@ class BakedScene:
             materials=self.materials.view(np.uint8).reshape(-1, 96),
         )
 
+    def save_rptw(self, path: str, atlas: np.ndarray | None = None) -> None:
+        """Flat little-endian container read by the C++ host (host/trace.cpp, World::from_path)."""
+        aw, ah = (0, 0) if atlas is None else (atlas.shape[1], atlas.shape[0])
+        with open(path, "wb") as f:
+            f.write(b"RPTW0001")
+            f.write(np.array([len(self.vertices), len(self.indices), len(self.materials), aw, ah], "<u4").tobytes())
+            for arr, dt in ((self.vertices, "<f4"), (self.normals, "<f4"), (self.tangents, "<f4"), (self.uvs, "<f4"), (self.indices, "<u4")):
+                f.write(np.ascontiguousarray(arr, dt).tobytes())
+            f.write(np.ascontiguousarray(self.materials).tobytes())
+            if atlas is not None:
+                f.write(np.ascontiguousarray(atlas, np.uint8).tobytes())
+
     @staticmethod
     def load(path: str) -> "BakedScene":
         z = np.load(path)

@@ -176,3 +176,121 @@ def test_error_codes():
         with pytest.raises(capi.RptError) as e:
             r.write_rng(np.zeros((10, 2), np.uint32))
         assert e.value.code == capi.ERR_SIZE_MISMATCH
+
+
+# ---------------------------------------------------------------------------- edge cases
+def _tiny_world():
+    """One emissive-free triangle in front of the camera: the BVH root is a leaf (intersection.rs:182-186)."""
+    from rust_path_tracer_b200.glb import MATERIAL_DTYPE, BakedScene
+    from rust_path_tracer_b200.world import World
+
+    v = np.array([[-1.5, 0.2, 2, 1], [1.5, 0.2, 2, 1], [0, 2.4, 2, 1]], np.float32)
+    n = np.array([[0, 0, -1, 0]] * 3, np.float32)
+    mats = np.zeros(1, MATERIAL_DTYPE)
+    mats[0]["albedo"] = (0.7, 0.5, 0.3, 1)
+    mats[0]["roughness"] = 0.6
+    scene = BakedScene(v, n, np.zeros((3, 4), np.float32), np.zeros((3, 2), np.float32), np.array([[0, 1, 2, 0]], np.uint32), mats)
+    return World.from_baked(scene)
+
+
+@pytest.mark.parametrize("w,h", [(33, 17), (1, 1), (8, 130)])
+def test_odd_frame_sizes(w, h):
+    """Frames that are not multiples of the 8x8 tile / 32-lane warp (the reference's own bounds check is off
+    by one there, lib.rs:205); every pixel must still get exactly one sample per pass."""
+    world = helpers.world("DarkCornell")
+    cfg = helpers.config(w, h, 1)
+    seeds = helpers.seeds(w, h)
+    o_out, o_rng, o_ids, _ = render_oracle(world, cfg, seeds, 4)
+    for pipeline in (capi.PIPELINE_WAVEFRONT, capi.PIPELINE_MEGAKERNEL):
+        c_out, c_rng, c_ids, _ = render_cuda(world, cfg, seeds, 4, pipeline)
+        np.testing.assert_array_equal(c_rng, o_rng)
+        np.testing.assert_array_equal(c_ids, o_ids)
+        assert helpers.mae(c_out[:, :3] / 4, o_out[:, :3] / 4)[0] <= MAE_TOLERANCE
+
+
+def test_single_triangle_scene_and_sky_fallback():
+    world = _tiny_world()
+    assert len(world.nodes) == 1 and world.light_pick_buffer[0]["ratio"] < 0  # leaf root, "no lights" sentinel
+    for has_sky in (0, 1):  # 1 with no image supplied: the 2x2 magenta fallback (src/asset.rs:275-290)
+        cfg = helpers.config(64, 48, 1, has_skybox=has_sky)
+        seeds = helpers.seeds(64, 48)
+        o_out, _, o_ids, _ = render_oracle(world, cfg, seeds, 8)
+        assert (o_ids == 0).any() and (o_ids == 0xFFFFFFFF).any()
+        for pipeline in (capi.PIPELINE_WAVEFRONT, capi.PIPELINE_MEGAKERNEL):
+            c_out, _, c_ids, _ = render_cuda(world, cfg, seeds, 8, pipeline)
+            np.testing.assert_array_equal(c_ids, o_ids)
+            assert helpers.mae(c_out[:, :3] / 8, o_out[:, :3] / 8)[0] <= MAE_TOLERANCE
+
+
+def test_russian_roulette_and_uniform_seeds():
+    """min_bounces = 0 makes Russian roulette fire from bounce 1 (lib.rs:175-181); seeds in uniform mode
+    (x random, y = 0, src/trace.rs:158)."""
+    from rust_path_tracer_b200.world import make_rng_seeds
+
+    world = helpers.world("VeachMIS")
+    cfg = helpers.config(96, 54, 0, min_bounces=0, max_bounces=6)
+    seeds = make_rng_seeds(96, 54, use_blue_noise=False, uniform_seed=42)
+    assert (seeds[:, 1] == 0).all() and len(np.unique(seeds[:, 0])) > 5000
+    o_out, o_rng, o_ids, o_ctr = render_oracle(world, cfg, seeds, 16)
+    for pipeline in (capi.PIPELINE_WAVEFRONT, capi.PIPELINE_MEGAKERNEL):
+        c_out, c_rng, c_ids, c_ctr = render_cuda(world, cfg, seeds, 16, pipeline)
+        np.testing.assert_array_equal(c_rng, o_rng)
+        np.testing.assert_array_equal(c_ids, o_ids)
+        assert helpers.mae(c_out[:, :3] / 16, o_out[:, :3] / 16)[0] <= MAE_TOLERANCE
+        assert abs(c_ctr["nearest_rays"] / o_ctr["nearest_rays"] - 1) < 5e-3
+
+
+def test_resume_from_previous_framebuffer():
+    """"continue previous" (src/trace.rs:163-164): the accumulator is re-seeded as framebuffer x samples."""
+    world = helpers.world("DarkCornell")
+    cfg = helpers.config(48, 32, 1)
+    seeds = helpers.seeds(48, 32)
+    init = np.random.default_rng(0).random((48 * 32, 4)).astype(np.float32)
+    init[:, 3] = 5.0
+    with Renderer(0) as r:
+        r.upload_world(world); r.set_config(cfg); r.write_rng(seeds)
+        r.enqueue(4)
+        fresh = r.read_output()
+        r.write_rng(seeds); r.write_output(init)
+        r.enqueue(4)
+        resumed = r.read_output()
+    np.testing.assert_allclose(resumed, init + fresh, rtol=2e-6, atol=1e-6)
+
+
+def test_tile_partition_on_one_gpu():
+    """rpt_set_tile_partition: two contexts rendering complementary 32x32 tile sets reproduce the full frame
+    bit for bit (the multi-GPU tile split without the NCCL step)."""
+    world = helpers.world("VeachMIS")
+    cfg = helpers.config(100, 70, 1)
+    seeds = helpers.seeds(100, 70)
+    full, *_ = render_cuda(world, cfg, seeds, 4, capi.PIPELINE_WAVEFRONT)
+    for pipeline in (capi.PIPELINE_WAVEFRONT, capi.PIPELINE_MEGAKERNEL):
+        total = np.zeros_like(full)
+        for rank in range(3):
+            with Renderer(0, pipeline) as r:
+                r.upload_world(world); r.set_config(cfg); r.set_tile_partition(rank, 3); r.write_rng(seeds)
+                r.enqueue(4)
+                part = r.read_output()
+                assert r.counters()["paths"] == int((part[:, 3] > 0).sum()) * 4
+            assert ((part[:, 3] == 0) | (part[:, 3] == 4)).all()
+            total += part
+        if pipeline == capi.PIPELINE_WAVEFRONT:
+            np.testing.assert_array_equal(total, full)
+        else:
+            assert helpers.mae(total[:, :3] / 4, full[:, :3] / 4)[0] <= 1e-6
+
+
+def test_golden_vectors():
+    """The committed oracle outputs (tests/golden/*.npz) — no oracle run needed on the GPU box."""
+    import glob
+
+    from rust_path_tracer_b200.capi import TracingConfig
+
+    for path in sorted(glob.glob(helpers.GOLDEN_DIR + "/*.npz")):
+        z = np.load(path)
+        cfg = TracingConfig.from_buffer_copy(z["config"].tobytes())
+        world = helpers.world(str(z["scene"]))
+        spp = int(z["spp"])
+        out, _, ids, ctr = render_cuda(world, cfg, helpers.seeds(cfg.width, cfg.height), spp, capi.PIPELINE_WAVEFRONT)
+        assert float((ids != z["primary_ids"]).mean()) <= ID_MISMATCH_BUDGET, path
+        assert helpers.mae(out[:, :3] / spp, z["output"][:, :3] / spp)[0] <= MAE_TOLERANCE, path
