@@ -138,15 +138,24 @@ def load_workload(name):
     return world, cfg, make_rng_seeds(w, h), spp, label, scene, sky
 
 
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_sample(world, cfg, seeds, spp, threads=0, sky=None):
-    """Time the CPU oracle on `spp` samples of the workload; returns (seconds, counters)."""
+    """Time the CPU oracle on `spp` samples of the workload; returns (seconds, counters, threads used)."""
+    threads = threads or host_threads()
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import oracle as oracle_mod
 
     scene = oracle_mod.OracleScene(world, sky)
     t0 = time.perf_counter()
     _, _, ctr, _ = oracle_mod.trace(cfg, scene, seeds, spp, threads=threads)
-    return time.perf_counter() - t0, ctr, oracle_mod.max_threads() if threads == 0 else threads
+    return time.perf_counter() - t0, ctr, threads
 
 
 def run_reference(args):
@@ -301,7 +310,8 @@ def run_b200(args):
             "stage_ms": {k: v[0] for k, v in stages.items() if v[1]},
             "note": "scene is L2-resident: algorithmic bytes are served by L1/L2, so frac can exceed DRAM traffic; see DESIGN.md",
         }
-        # ---- CPU baseline: the oracle port on the host cores, bounded sample ------------------
+    if rank == 0 and not args.quick and dist is None:
+        # ---- CPU baseline (N = 1 only): the oracle port on the host cores, bounded sample -----
         cpu_spp = max(1, min(8, int(15.0 / max(dt1, 1e-3))))
         dtc, cctr, threads = oracle_sample(world, cfg, seeds0, cpu_spp, sky=sky)
         line["cpu_baseline"] = {"value": npix * cpu_spp / dtc / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "port",
