@@ -49,7 +49,9 @@ class Collapser {
     bool subtree_ranges() {
         sub_first_.assign(nnodes_, 0u);
         sub_count_.assign(nnodes_, 0u);
-        std::vector<uint32_t> order, todo{0u};
+        std::vector<uint32_t>& order = order_;
+        order.clear();
+        std::vector<uint32_t> todo{0u};
         order.reserve(nnodes_);
         std::vector<uint8_t> seen(nnodes_, 0);
         while (!todo.empty()) {
@@ -81,8 +83,68 @@ class Collapser {
         return true;
     }
 
+    // Which binary nodes become wide nodes?  Every wide node a ray enters costs one 80-byte fetch and eight
+    // box tests whether its slots are full or not, so the collapse minimises the summed surface area of the
+    // wide nodes (the expected number of node visits of a random ray) instead of opening the largest child
+    // greedily — the dynamic programme of Ylitie, Karras & Laine 2017 (section 3.1) with all leaf terms
+    // constant (the reference's leaves are kept as they are):
+    //   forest(n, j) = cheapest way to present subtree n as at most j children of some wide node
+    //   forest(n, 1) = inner(n) = area(n) + min_k forest(left, k) + forest(right, 8 - k)   (n becomes a wide node)
+    //   forest(n, j) = min(forest(n, j-1), min_k forest(left, k) + forest(right, j - k))
+    // and a leaf costs nothing however many slots it is offered.
+    void plan_collapse(const std::vector<uint32_t>& order) {
+        plan_cost_.assign((size_t)nnodes_ * 8, 0.0f);   // [n*8 + j], j = 1..7
+        plan_split_.assign((size_t)nnodes_ * 8, 0);     // left share k for forest(n, j); 0 = "same as j-1" / "be a wide node"
+        plan_root_split_.assign(nnodes_, 4);
+        for (size_t idx = order.size(); idx-- > 0;) {
+            const uint32_t n = order[idx];
+            if (is_leaf_item(n)) continue;  // cost 0 for every j
+            const uint32_t l = nodes_[n].left_or_first, r = l + 1;
+            const float* cl = &plan_cost_[(size_t)l * 8];
+            const float* cr = &plan_cost_[(size_t)r * 8];
+            float* cn = &plan_cost_[(size_t)n * 8];
+            uint8_t* sn = &plan_split_[(size_t)n * 8];
+            Box3 b;
+            std::memcpy(b.lo, nodes_[n].aabb_min, 12);
+            std::memcpy(b.hi, nodes_[n].aabb_max, 12);
+            float best = INFINITY;
+            int best_k = 4;
+            for (int k = 1; k <= 7; ++k) {
+                const float c = cl[k] + cr[8 - k];
+                if (c < best) { best = c; best_k = k; }
+            }
+            plan_root_split_[n] = (uint8_t)best_k;
+            cn[1] = (float)b.half_area() + best;
+            sn[1] = 0;
+            for (int j = 2; j <= 7; ++j) {
+                cn[j] = cn[j - 1];
+                sn[j] = 0;
+                for (int k = 1; k < j; ++k) {
+                    const float c = cl[k] + cr[j - k];
+                    if (c < cn[j]) { cn[j] = c; sn[j] = (uint8_t)k; }
+                }
+            }
+        }
+    }
+    bool is_leaf_item(uint32_t n) const { return nodes_[n].triangle_count > 0 || (sub_count_[n] != 0 && sub_count_[n] <= leaf_merge_); }
+    // Children that present binary subtree n as at most j slots, following the plan.
+    bool collect(uint32_t n, int j, std::vector<Item>& out) const {
+        if (n >= nnodes_ || j < 1) return false;
+        while (!is_leaf_item(n) && j > 1 && plan_split_[(size_t)n * 8 + j] == 0) --j;  // "same as j-1"
+        Item it;
+        if (is_leaf_item(n) || j == 1) {
+            if (!node_item(n, it)) return false;
+            out.push_back(it);
+            return true;
+        }
+        const int k = plan_split_[(size_t)n * 8 + j];
+        const uint32_t l = nodes_[n].left_or_first;
+        return collect(l, k, out) && collect(l + 1, j - k, out);
+    }
+
     bool run(const char** error) {
         if (!subtree_ranges()) { *error = "malformed BVH: child index out of range or node referenced twice"; return false; }
+        if (use_dp_) plan_collapse(order_);
         out_.nodes.clear();
         out_.tri_pos.clear();
         out_.orig_index.clear();
@@ -102,20 +164,28 @@ class Collapser {
             queue.pop_front();
             out_.max_depth = std::max(out_.max_depth, w.depth);
 
-            // ---- gather up to 8 children by repeatedly opening the largest splittable one
+            // ---- gather up to 8 children
             std::vector<Item> kids;
-            if (splittable(w.item)) {
+            if (use_dp_ && !w.item.is_range && !plan_cost_.empty()) {
+                // the cut of this binary subtree chosen by the surface-area dynamic programme (plan_collapse)
+                const uint32_t l = nodes_[w.item.first].left_or_first;
+                const int kl = plan_root_split_[w.item.first];
+                if (!collect(l, kl, kids) || !collect(l + 1, 8 - kl, kids)) { *error = "malformed BVH: child index or triangle range out of bounds"; return false; }
+            } else if (splittable(w.item)) {
                 Item a, b;
                 if (!split(w.item, a, b)) { *error = "malformed BVH: child index or triangle range out of bounds"; return false; }
                 kids = {a, b};
             } else {
                 kids = {w.item};
             }
+            // top up greedily (opens over-full leaf runs; the whole job when the DP is off): largest box first
             while (kids.size() < 8) {
                 int best = -1;
                 double best_area = -1.0;
-                for (size_t i = 0; i < kids.size(); ++i)
-                    if (splittable(kids[i]) && kids[i].box.half_area() > best_area) { best = (int)i; best_area = kids[i].box.half_area(); }
+                for (size_t i = 0; i < kids.size(); ++i) {
+                    const bool open = use_dp_ && !plan_cost_.empty() ? (kids[i].is_range && kids[i].count > 3) : splittable(kids[i]);
+                    if (open && kids[i].box.half_area() > best_area) { best = (int)i; best_area = kids[i].box.half_area(); }
+                }
                 if (best < 0) break;
                 Item a, b;
                 if (!split(kids[best], a, b)) { *error = "malformed BVH: child index or triangle range out of bounds"; return false; }
@@ -298,10 +368,13 @@ class Collapser {
     const RptPerVertexData* verts_;
     uint32_t nverts_;
     WideBvh& out_;
-    std::vector<uint32_t> sub_first_, sub_count_;
+    std::vector<uint32_t> sub_first_, sub_count_, order_;
+    std::vector<float> plan_cost_;
+    std::vector<uint8_t> plan_split_, plan_root_split_;
 
   public:
     uint32_t leaf_merge_ = 1;  // largest binary subtree (in triangles) folded into one leaf slot; 1 = off
+    bool use_dp_ = true;       // surface-area dynamic programme (plan_collapse) vs. greedy largest-box-first
 };
 
 }  // namespace
@@ -318,6 +391,7 @@ bool build_wide_bvh(const RptBVHNode* nodes, uint32_t nnodes, const uint32_t* tr
             if (triangles[4 * t + k] >= nvertices) { *error = "triangle references a vertex out of range"; return false; }
     out = WideBvh{};
     Collapser c(nodes, nnodes, triangles, ntriangles, vertices, nvertices, out);
+    if (const char* v = std::getenv("RPT_COLLAPSE")) c.use_dp_ = std::strcmp(v, "greedy") != 0;
     if (const char* v = std::getenv("RPT_LEAF_MERGE")) c.leaf_merge_ = (uint32_t)std::min(3, std::max(1, std::atoi(v)));
     return c.run(error);
 }
