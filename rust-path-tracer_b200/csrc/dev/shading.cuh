@@ -27,7 +27,13 @@ RPT_D int f32_as_i32_sat(float f) {
     if (f <= -2147483648.0f) return (-2147483647 - 1);
     return (int)f;
 }
-RPT_D uint32_t wrap_coord(int c, uint32_t size) { return (uint32_t)((unsigned long long)(long long)c % (unsigned long long)size); }
+// `coord as usize % size`: a negative i32 sign-extends to a huge usize first.  Non-negative coordinates (the
+// only ones valid uvs produce) take a 32-bit path — a mask for power-of-two sizes; the 64-bit modulo (~100
+// instructions) is kept for the negative case only.
+RPT_D uint32_t wrap_coord(int c, uint32_t size) {
+    if (c >= 0) return (size & (size - 1u)) == 0u ? ((uint32_t)c & (size - 1u)) : ((uint32_t)c % size);
+    return (uint32_t)((unsigned long long)(long long)c % (unsigned long long)size);
+}
 
 struct TexelRGBA8 {
     const uchar4* texels;
