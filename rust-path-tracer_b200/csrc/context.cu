@@ -94,7 +94,6 @@ struct rpt_context {
     // trace-kernel tunables (defaults chosen on B200; RPT_* env vars override for sweeps)
     int trace_blocks_per_sm = 8;
     int refill_below = 20;
-    float postpone_frac = 0.0f;
 
     // scene, reference layouts (megakernel arm)
     DevBuf<RptPerVertexData> d_vertices;
@@ -239,7 +238,7 @@ MegaParams mega_params(const rpt_context* c) {
 
 WideWorld wide_world(const rpt_context* c) {
     WideWorld w{};
-    w.bvh = WideScene{c->d_wide_nodes.p, c->d_tri_pos.p};
+    w.bvh = WideScene{c->d_wide_nodes.p, c->d_tri_pos.p, kHalf1024Bytes};
     w.tri_shade = c->d_tri_shade.p;
     w.tri_tangent = c->d_tri_tangent.p;
     w.materials = c->d_materials.p;
@@ -310,7 +309,7 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
     const FrameParams f = frame_params(c);
     const WideWorld w = wide_world(c);
     const WaveState s = wave_state(c);
-    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below, c->postpone_frac};
+    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below};
     const uint32_t nslots = d.npix * d.k_samples;
     c->launch(RPT_STAGE_OTHER, [&] { launch_wf_reset(l, s, 1, true); });
     c->launch(RPT_STAGE_GENERATE, [&] { launch_wf_generate(l, f, s, d, c->d_rng.p); });
@@ -389,7 +388,6 @@ extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
     c->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("RPT_TRACE_BLOCKS_PER_SM")) c->trace_blocks_per_sm = std::max(1, atoi(v));
     if (const char* v = getenv("RPT_REFILL_BELOW")) c->refill_below = atoi(v);
-    if (const char* v = getenv("RPT_POSTPONE_FRAC")) c->postpone_frac = (float)atof(v);
     if (const char* v = getenv("RPT_WAVE_SLOTS")) c->wave_slots = (uint32_t)std::max(1024, atoi(v));
     *out_ctx = c;
     return RPT_OK;

@@ -109,7 +109,6 @@ struct WaveLaunch {
     cudaStream_t stream;
     int trace_blocks_per_sm;  // resident 128-thread blocks per SM of the trace kernels
     int refill_below;         // refill idle lanes once fewer than this many lanes of a warp hold a ray
-    float postpone_frac;      // postpone triangle tests while fewer than this fraction of live lanes have any
 };
 
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole);

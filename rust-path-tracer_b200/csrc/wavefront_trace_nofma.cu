@@ -22,6 +22,8 @@ constexpr int kTraceWarps = kTraceBlock / 32;
 struct SmemStack {
     uint2* column;  // this lane's column of the warp slab; entries are 32 lanes apart
     int n;
+    const uint8_t* perm;  // the block's octant permutation table, [octant][child set]
+    __device__ __forceinline__ uint32_t permute(uint32_t oct, uint32_t m) const { return perm[oct * 256u + m]; }
     __device__ __forceinline__ void push(uint2 v) {
         if (n < (int)kWideStackCapacity) column[n * 32] = v;  // depth is validated at upload; never drop silently there
         ++n;
@@ -71,16 +73,16 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(FrameParams f, WaveSta
 // Lanes pull rays one at a time from a device-side cursor: when a lane's ray terminates it waits
 // only until the warp's live-lane count drops below `refill_below`, then every idle lane is handed
 // a new ray (ray refill keeps the warp full although rays need very different numbers of steps).
-// Inside the traversal loop a lane that reaches triangles while fewer than `postpone_frac` of the
-// live lanes have any pushes the triangle group back on its stack and goes on with nodes first
-// (triangle postponing), so ray/triangle tests execute with more lanes enabled.
 
 constexpr uint32_t kMissRecord = 0xFFFFFFFFu;  // hit[].y of a ray that hit nothing (triangle indices are < 2^31)
 
 template <bool NEAREST>
-__global__ void __launch_bounds__(kTraceBlock) wf_trace_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
-                                                               int refill_below, float postpone_frac) {
+__global__ void __launch_bounds__(kTraceBlock, 8) wf_trace_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
+                                                               int refill_below) {
     __shared__ uint2 slabs[kTraceWarps][kWideStackCapacity][32];
+    __shared__ uint8_t perm_table[8 * 256];
+    for (uint32_t i = threadIdx.x; i < 8u * 256u; i += kTraceBlock) perm_table[i] = (uint8_t)octant_permute(i >> 8, i & 0xFFu);
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     // (ternaries, not s.q_ext[in_queue]: dynamic indexing would force the parameter block into local memory)
     const uint32_t n = NEAREST ? (identity ? n_identity : (in_queue ? s.ctl->n_ext[1] : s.ctl->n_ext[0])) : s.ctl->n_shadow;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(kTraceBlock) wf_trace_kernel(WideScene bvh, Wa
     uint32_t* fetch = NEAREST ? &s.ctl->fetch_extend : &s.ctl->fetch_shadow;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.counters + (NEAREST ? 1 : 2), (unsigned long long)n);
 
-    SmemStack st{&slabs[warp][0][lane], 0};
+    SmemStack st{&slabs[warp][0][lane], 0, perm_table};
     WideCursor<NEAREST> c;
     uint32_t item = 0;       // path slot (NEAREST) / shadow-queue index (ANY)
     bool busy = false;       // this lane holds an unfinished ray
@@ -132,17 +134,9 @@ __global__ void __launch_bounds__(kTraceBlock) wf_trace_kernel(WideScene bvh, Wa
         // ---- traverse until the ray ends or the warp wants a refill ---------------------------
         while (busy) {
             bool finished = false;
-            if (c.has_nodes()) c.visit_node(bvh, st);
-            else c.take_triangle_group();
-            const int live = __popc(__activemask());
-            while (c.has_triangles()) {
-                if ((float)__popc(__activemask()) < postpone_frac * (float)live && (c.has_nodes() || !st.empty())) {
-                    st.push(c.tgroup);  // postponed: comes back through advance() / take_triangle_group()
-                    c.tgroup.y = 0u;
-                    break;
-                }
+            if (c.has_nodes()) c.visit_node(bvh, st);  // (only a non-finite ray starts without nodes)
+            while (c.has_triangles())
                 if (c.test_triangle(bvh)) { finished = true; break; }
-            }
             if (!finished && !c.advance(st)) finished = true;
             if (finished) {
                 busy = false;
@@ -217,11 +211,11 @@ void launch_wf_generate(const WaveLaunch& l, const FrameParams& f, const WaveSta
     wf_generate_kernel<<<l.grid * 2, 256, 0, l.stream>>>(f, s, d, rng);
 }
 void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, int in_queue, bool identity_queue, uint32_t n_identity) {
-    wf_trace_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.postpone_frac);
+    wf_trace_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below);
     wf_compact_kernel<<<l.grid * 4, 256, 0, l.stream>>>(s, in_queue, identity_queue, n_identity);
 }
 void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState& s) {
-    wf_trace_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.postpone_frac);
+    wf_trace_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below);
 }
 void launch_wf_export_primary(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, const WaveDesc& d, uint32_t* ids) {
     wf_export_primary_kernel<<<(d.npix + 255) / 256, 256, 0, l.stream>>>(bvh, s, d, ids);

@@ -5,13 +5,15 @@
 //   quantised to 8 bits per plane on a per-node power-of-two grid anchored at the node's min
 //   corner (conservative: lo floored, hi ceiled); children sit in octant-ordered slots so a
 //   ray's visiting order is `slot ^ octant` with no distance sort.
-//       word 0: origin.x, origin.y, origin.z (f32), [ex | ey<<8 | ez<<16 | inner_mask<<24]
-//       word 1: first_child_node, first_triangle, meta[0..3], meta[4..7]
+//       word 0: origin.x, origin.y, origin.z, cell.x (f32; cells are powers of two)
+//       word 1: first_child_node, first_triangle, [valid_triangles (24 bits) | inner_mask<<24],
+//               [upper half of cell.y's bits | upper half of cell.z's bits << 16]
 //       word 2: qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7]
 //       word 3: qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7]
 //       word 4: qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7]
-//   meta[i]: 0 = empty; inner child = 0b001'11sss (24 + slot); leaf = (unary triangle count
-//   1/3/7) << 5 | offset of its first triangle in the node's triangle block (< 24).
+//   A slot is an inner child (its inner_mask bit; child nodes are contiguous in slot order), a leaf
+//   of 1..3 triangles (valid_triangles bits 3*slot .. 3*slot+2 set in unary; the node's triangles
+//   are contiguous in bit order, so bit k is triangle first_triangle + popc(valid below k)), or empty.
 // * triangle position stream, in wide-leaf order, 3 x float4 per triangle:
 //       (a.xyz, bits(reference triangle index)), (e1 = b-a, bits(material)), (e2 = c-a, 0)
 //   e1/e2 are single IEEE subtractions done on the host, so the device-side ray/triangle test

@@ -203,27 +203,23 @@ class Collapser {
             // ---- allocate children: inner nodes contiguous in slot order, triangles in one block
             const uint32_t child_base = (uint32_t)out_.nodes.size();
             const uint32_t tri_base = (uint32_t)out_.orig_index.size();
-            uint32_t imask = 0, meta[8] = {0}, tri_off = 0;
+            uint32_t imask = 0, valid = 0;
             for (int s = 0; s < 8; ++s) {
                 const int k = kid_in_slot[s];
                 if (k < 0) continue;
                 const Item& it = kids[k];
                 if (splittable(it)) {
                     imask |= 1u << s;
-                    meta[s] = (1u << 5) | (24u + (uint32_t)s);
                     out_.nodes.emplace_back();
                     queue.push_back({(uint32_t)out_.nodes.size() - 1u, it, w.depth + 1u});
                     out_.inner_children++;
                 } else {
-                    const uint32_t unary = it.count == 1 ? 1u : (it.count == 2 ? 3u : 7u);
-                    meta[s] = (unary << 5) | tri_off;
+                    valid |= (it.count == 1 ? 1u : (it.count == 2 ? 3u : 7u)) << (3 * s);  // slot s owns triangle bits 3s..3s+2
                     for (uint32_t t = 0; t < it.count; ++t) emit_triangle(it.first + t);
-                    tri_off += it.count;
                     out_.leaf_children++;
                 }
             }
-            if (tri_off > 24) { *error = "internal: more than 24 triangles under one wide node"; return false; }
-            encode(out_.nodes[w.wide], nb, kids, kid_in_slot, child_base, tri_base, imask, meta);
+            encode(out_.nodes[w.wide], nb, kids, kid_in_slot, child_base, tri_base, imask, valid);
         }
         for (uint32_t t = 0; t < ntris_; ++t)
             if (out_.wide_index[t] == 0xFFFFFFFFu) { *error = "malformed BVH: a triangle is not referenced by any leaf"; return false; }
@@ -320,7 +316,7 @@ class Collapser {
     }
 
     static void encode(WideNode& node, const Box3& nb, const std::vector<Item>& kids, const int* kid_in_slot, uint32_t child_base,
-                       uint32_t tri_base, uint32_t imask, const uint32_t* meta) {
+                       uint32_t tri_base, uint32_t imask, uint32_t valid) {
         uint8_t e[3];
         double cell[3];
         for (int k = 0; k < 3; ++k) {
@@ -348,14 +344,12 @@ class Collapser {
             }
         }
         auto pack4 = [](const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
-        uint8_t m8[8];
-        for (int s = 0; s < 8; ++s) m8[s] = (uint8_t)meta[s];
         uint32_t* w = node.w;
         std::memcpy(&w[0], &nb.lo[0], 4);
         std::memcpy(&w[1], &nb.lo[1], 4);
         std::memcpy(&w[2], &nb.lo[2], 4);
-        w[3] = (uint32_t)e[0] | ((uint32_t)e[1] << 8) | ((uint32_t)e[2] << 16) | (imask << 24);
-        w[4] = child_base; w[5] = tri_base; w[6] = pack4(m8); w[7] = pack4(m8 + 4);
+        w[3] = (uint32_t)e[0] << 23;  // the cell sizes as float bits: x whole, y and z as their upper halves
+        w[4] = child_base; w[5] = tri_base; w[6] = valid | (imask << 24); w[7] = ((uint32_t)e[1] << 7) | ((uint32_t)e[2] << 23);
         w[8] = pack4(q[0]); w[9] = pack4(q[0] + 4); w[10] = pack4(q[1]); w[11] = pack4(q[1] + 4);
         w[12] = pack4(q[2]); w[13] = pack4(q[2] + 4); w[14] = pack4(q[3]); w[15] = pack4(q[3] + 4);
         w[16] = pack4(q[4]); w[17] = pack4(q[4] + 4); w[18] = pack4(q[5]); w[19] = pack4(q[5] + 4);

@@ -20,6 +20,7 @@ struct LocalStack {
     void push(rpt::uint2 v) { data[n++] = v; if (n > high_water) high_water = n; }
     rpt::uint2 pop() { return data[--n]; }
     bool empty() const { return n == 0; }
+    uint32_t permute(uint32_t oct, uint32_t m) const { return rpt::octant_permute(oct, m); }
 };
 }  // namespace
 
@@ -32,7 +33,7 @@ int harness_wide_intersect(const RptPerVertexData* verts, uint32_t nverts, const
     rpt::WideBvh wide;
     const char* err = "";
     if (!rpt::build_wide_bvh(nodes, nnodes, tris, ntris, verts, nverts, wide, &err)) return -1;
-    rpt::WideScene scene{reinterpret_cast<const rpt::uint4*>(wide.nodes.data()), reinterpret_cast<const rpt::float4*>(wide.tri_pos.data())};
+    rpt::WideScene scene{reinterpret_cast<const rpt::uint4*>(wide.nodes.data()), reinterpret_cast<const rpt::float4*>(wide.tri_pos.data()), rpt::kHalf1024Bytes};
     int high = 0;
     for (uint32_t i = 0; i < nrays; ++i) {
         const float* r = rays_o_d + 6 * (size_t)i;
