@@ -30,6 +30,11 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// Path slots per wave.  Every stage is a persistent kernel whose last blocks drain alone, so long waves amortise
+// the launch tails (measured: 4 Mi -> 16 Mi slots = +4% Mpaths/s on the 1080p workloads); 16 Mi slots are 2.6 GB of
+// path state, nothing next to 180 GB of HBM.  kShadedSlotMask caps a wave below 2^30 slots.
+constexpr uint32_t kDefaultWaveSlots = 1u << 24, kMaxWaveSlots = (1u << 30) - 1u;
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -90,10 +95,13 @@ struct rpt_context {
     cudaStream_t stream = nullptr;
     std::string error;
     int pipeline = RPT_PIPELINE_WAVEFRONT;
-    uint32_t wave_slots = 1u << 22;
+    uint32_t wave_slots = kDefaultWaveSlots;
     // trace-kernel tunables (defaults chosen on B200; RPT_* env vars override for sweeps)
     int trace_blocks_per_sm = 8;
     int refill_below = 20;
+    bool pooled_triangles = false;
+    uint32_t flush_at = 32;
+    int flush_waiting = 8;
 
     // scene, reference layouts (megakernel arm)
     DevBuf<RptPerVertexData> d_vertices;
@@ -131,7 +139,7 @@ struct rpt_context {
     uint32_t wave_capacity = 0;
     DevBuf<float4> w_ray_o, w_ray_d, w_thr, w_rad, w_mis_a, w_mis_b, w_sh_o, w_sh_d, w_sh_c;
     DevBuf<uint2> w_hit;
-    DevBuf<uint32_t> w_q0, w_q1, w_qhit, w_qmiss;
+    DevBuf<uint32_t> w_q0, w_q1, w_qhit, w_qmiss, w_qshaded, w_qshadow;
     DevBuf<WaveCtl> w_ctl;
     DevBuf<unsigned long long> d_counters;
 
@@ -207,8 +215,8 @@ FrameParams frame_params(const rpt_context* c) {
     f.clamp_hi = c->config.specular_weight_clamp[1];
     f.sun_dir = mk3(c->config.sun_direction[0], c->config.sun_direction[1], c->config.sun_direction[2]);
     f.sun_intensity = c->config.sun_direction[3];
-    f.sky = SkyImage{c->d_sky.p, c->sky_w, c->sky_h, c->sky_yaw_sin, c->sky_yaw_cos, c->config.sun_direction[3] * (1.0f / 15.0f)};
-    f.atlas = Atlas{c->d_atlas.p, c->atlas_w, c->atlas_h};
+    f.sky = SkyImage{c->d_sky.p, c->sky_w, c->sky_h, pow2_mask(c->sky_w), pow2_mask(c->sky_h), c->sky_yaw_sin, c->sky_yaw_cos, c->config.sun_direction[3] * (1.0f / 15.0f)};
+    f.atlas = Atlas{c->d_atlas.p, c->atlas_w, c->atlas_h, pow2_mask(c->atlas_w), pow2_mask(c->atlas_h)};
     f.tile_rank = c->tile_rank;
     f.tile_count = c->tile_count;
     return f;
@@ -255,6 +263,7 @@ WaveState wave_state(rpt_context* c) {
     s.mis_a = c->w_mis_a.p; s.mis_b = c->w_mis_b.p; s.hit = c->w_hit.p;
     s.sh_o = c->w_sh_o.p; s.sh_d = c->w_sh_d.p; s.sh_c = c->w_sh_c.p;
     s.q_ext[0] = c->w_q0.p; s.q_ext[1] = c->w_q1.p; s.q_hit = c->w_qhit.p; s.q_miss = c->w_qmiss.p;
+    s.q_shaded = c->w_qshaded.p; s.q_shadow = c->w_qshadow.p;
     s.ctl = c->w_ctl.p;
     s.counters = c->d_counters.p;
     return s;
@@ -267,6 +276,7 @@ int ensure_wave(rpt_context* c, uint32_t slots) {
     RPT_CUDA(c, c->w_sh_o.alloc(slots)); RPT_CUDA(c, c->w_sh_d.alloc(slots)); RPT_CUDA(c, c->w_sh_c.alloc(slots));
     RPT_CUDA(c, c->w_hit.alloc(slots));
     RPT_CUDA(c, c->w_q0.alloc(slots)); RPT_CUDA(c, c->w_q1.alloc(slots)); RPT_CUDA(c, c->w_qhit.alloc(slots)); RPT_CUDA(c, c->w_qmiss.alloc(slots));
+    RPT_CUDA(c, c->w_qshaded.alloc(slots)); RPT_CUDA(c, c->w_qshadow.alloc(slots));
     if (!c->w_ctl.p) RPT_CUDA(c, c->w_ctl.alloc(1));
     c->wave_capacity = slots;
     return RPT_OK;
@@ -309,7 +319,7 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
     const FrameParams f = frame_params(c);
     const WideWorld w = wide_world(c);
     const WaveState s = wave_state(c);
-    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below};
+    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below, c->pooled_triangles, c->flush_at, c->flush_waiting};
     const uint32_t nslots = d.npix * d.k_samples;
     c->launch(RPT_STAGE_OTHER, [&] { launch_wf_reset(l, s, 1, true); });
     c->launch(RPT_STAGE_GENERATE, [&] { launch_wf_generate(l, f, s, d, c->d_rng.p); });
@@ -325,7 +335,8 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
             break;
         }
         c->launch(RPT_STAGE_MISS, [&] { launch_wf_miss(l, f, s); });
-        c->launch(RPT_STAGE_SHADE, [&] { launch_wf_shade(l, f, w, s, d, c->d_rng.p, b, nxt); });
+        c->launch(RPT_STAGE_SHADE, [&] { launch_wf_shade(l, f, w, s, d, c->d_rng.p, b); launch_wf_compact_shaded(l, s, nxt); });
+        c->kernel_launches++;  // shade = shading + queue compaction
         if (f.nee != RPT_NEE_NONE && c->nbins > 0) c->launch(RPT_STAGE_SHADOW, [&] { launch_wf_shadow(l, w.bvh, s); });
     }
     if (!primary_only) c->launch(RPT_STAGE_ACCUMULATE, [&] { launch_wf_accumulate(l, s, d, c->d_rng.p, c->d_output.p); });
@@ -336,7 +347,7 @@ template <class Fn>
 int for_each_wave(rpt_context* c, uint32_t n_samples, Fn&& fn) {
     const uint32_t total = c->tile_count > 1 ? c->pixel_map_len : c->npixels();
     if (total == 0) return RPT_OK;
-    const uint32_t slots = std::max<uint32_t>(c->wave_slots, 1024u);
+    const uint32_t slots = std::min(std::max<uint32_t>(c->wave_slots, 1024u), kMaxWaveSlots);
     const uint32_t chunk = std::min(total, slots);
     for (uint32_t base = 0; base < total; base += chunk) {
         const uint32_t np = std::min(chunk, total - base);
@@ -388,6 +399,9 @@ extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
     c->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("RPT_TRACE_BLOCKS_PER_SM")) c->trace_blocks_per_sm = std::max(1, atoi(v));
     if (const char* v = getenv("RPT_REFILL_BELOW")) c->refill_below = atoi(v);
+    if (const char* v = getenv("RPT_POOLED_TRIANGLES")) c->pooled_triangles = atoi(v) != 0;
+    if (const char* v = getenv("RPT_FLUSH_AT")) c->flush_at = (uint32_t)std::min(32, std::max(1, atoi(v)));
+    if (const char* v = getenv("RPT_FLUSH_WAITING")) c->flush_waiting = std::max(1, atoi(v));
     if (const char* v = getenv("RPT_WAVE_SLOTS")) c->wave_slots = (uint32_t)std::max(1024, atoi(v));
     *out_ctx = c;
     return RPT_OK;
@@ -403,7 +417,8 @@ extern "C" int rpt_destroy(rpt_context* c) {
     for (auto* b : {&c->w_ray_o, &c->w_ray_d, &c->w_thr, &c->w_rad, &c->w_mis_a, &c->w_mis_b, &c->w_sh_o, &c->w_sh_d, &c->w_sh_c, &c->d_tri_pos,
                     &c->d_tri_shade, &c->d_tri_tangent, &c->d_sky, &c->d_output})
         b->release();
-    c->w_hit.release(); c->w_q0.release(); c->w_q1.release(); c->w_qhit.release(); c->w_qmiss.release(); c->w_ctl.release();
+    c->w_hit.release(); c->w_q0.release(); c->w_q1.release(); c->w_qhit.release(); c->w_qmiss.release(); c->w_qshaded.release();
+    c->w_qshadow.release(); c->w_ctl.release();
     c->d_counters.release(); c->d_vertices.release(); c->d_triangles.release(); c->d_nodes.release(); c->d_materials.release();
     c->d_lights.release(); c->d_atlas.release(); c->d_wide_nodes.release(); c->d_light_bins.release(); c->d_light_records.release();
     c->d_rng.release(); c->d_rgb.release(); c->d_ids.release(); c->d_pixel_map.release();
@@ -423,7 +438,7 @@ extern "C" int rpt_set_pipeline(rpt_context* c, int pipeline) {
 
 extern "C" int rpt_set_wave_slots(rpt_context* c, uint32_t slots) {
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
-    c->wave_slots = slots == 0 ? (1u << 22) : slots;
+    c->wave_slots = slots == 0 ? kDefaultWaveSlots : slots;
     return RPT_OK;
 }
 
@@ -435,7 +450,7 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
     if (!vertices || !triangles || !nodes || !materials || !lights || nvertices == 0 || ntriangles == 0 || nnodes == 0 || nmaterials == 0 || nlights == 0)
         return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: null or empty buffer");
-    if (ntriangles >= 0x80000000u) return c->fail(RPT_ERR_UNSUPPORTED, "more than 2^31 triangles");
+    if (ntriangles >= (1u << 27)) return c->fail(RPT_ERR_UNSUPPORTED, "more than 2^27 triangles (the trace kernel packs lane and triangle in one word)");
     if ((atlas_rgba8 && (atlas_w == 0 || atlas_h == 0)) || (sky_rgba32f && (sky_w == 0 || sky_h == 0)))
         return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: image with a zero dimension");
     for (size_t t = 0; t < (size_t)ntriangles; ++t)

@@ -21,25 +21,34 @@ struct f2 {
 // Manual bilinear, no half-texel shift, wrap by modulo (with the reference's `i32 as usize`
 // sign-extension), alpha ignored.  Texels are either RGBA8 (atlas; /255 like
 // dynamic_image_to_cpu_buffer, src/asset.rs:266-273) or float4 (sky).
-RPT_D int f32_as_i32_sat(float f) {
-    if (f != f) return 0;
-    if (f >= 2147483648.0f) return 2147483647;
-    if (f <= -2147483648.0f) return (-2147483647 - 1);
-    return (int)f;
-}
-// `coord as usize % size`: a negative i32 sign-extends to a huge usize first.  Non-negative coordinates (the
-// only ones valid uvs produce) take a 32-bit path — a mask for power-of-two sizes; the 64-bit modulo (~100
-// instructions) is kept for the negative case only.
-RPT_D uint32_t wrap_coord(int c, uint32_t size) {
-    if (c >= 0) return (size & (size - 1u)) == 0u ? ((uint32_t)c & (size - 1u)) : ((uint32_t)c % size);
+// Rust's `f32 as i32` saturates and maps NaN to 0 — exactly cvt.rzi.s32.f32.
+RPT_D int f32_as_i32_sat(float f) { return __float2int_rz(f); }
+// `coord as usize % size`: a negative i32 sign-extends to a huge usize first.  Images whose size is a power of
+// two (the 4096^2 atlas, lat-long skies) wrap non-negative coordinates — the only ones valid uvs produce — with
+// a mask (`mask` = size - 1, or 0 when the size is not a power of two); everything else takes the general path.
+static __device__ __noinline__ uint32_t wrap_coord_general(int c, uint32_t size) {
+    if (c >= 0) return (uint32_t)c % size;
     return (uint32_t)((unsigned long long)(long long)c % (unsigned long long)size);
+}
+RPT_D uint32_t wrap_coord(int c, uint32_t size, uint32_t mask) {
+    if (c >= 0 && mask != 0u) return (uint32_t)c & mask;
+    return wrap_coord_general(c, size);
+}
+RPT_HD uint32_t pow2_mask(uint32_t size) { return (size & (size - 1u)) == 0u ? size - 1u : 0u; }
+
+// x / 255 for an integer 0 <= x <= 255, correctly rounded (== the IEEE division the CPU path does, checked for all
+// 256 values in tests/test_abi.py) without the division's special-case machinery: one Newton step on x * (1/255).
+RPT_D float unorm8(uint32_t x) {
+    const float xf = (float)x, r = 1.0f / 255.0f;
+    const float q = xf * r;
+    return fmaf(fmaf(-q, 255.0f, xf), r, q);
 }
 
 struct TexelRGBA8 {
     const uchar4* texels;
     RPT_D f3 operator()(uint32_t i) const {
         const uchar4 t = __ldg(texels + i);
-        return mk3((float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f);
+        return mk3(unorm8(t.x), unorm8(t.y), unorm8(t.z));
     }
 };
 struct TexelF32 {
@@ -48,12 +57,12 @@ struct TexelF32 {
 };
 
 template <class Fetch>
-RPT_D f3 sample_bilinear(const Fetch& fetch, uint32_t width, uint32_t height, float u, float v) {
+RPT_D f3 sample_bilinear(const Fetch& fetch, uint32_t width, uint32_t height, uint32_t wmask, uint32_t hmask, float u, float v) {
     const float sx = u * (float)width, sy = v * (float)height;
     const float flx = floorf(sx), fly = floorf(sy);
     const float fx = sx - flx, fy = sy - fly;
-    const uint32_t x0 = wrap_coord(f32_as_i32_sat(flx), width), x1 = wrap_coord(f32_as_i32_sat(ceilf(sx)), width);
-    const uint32_t y0 = wrap_coord(f32_as_i32_sat(fly), height), y1 = wrap_coord(f32_as_i32_sat(ceilf(sy)), height);
+    const uint32_t x0 = wrap_coord(f32_as_i32_sat(flx), width, wmask), x1 = wrap_coord(f32_as_i32_sat(ceilf(sx)), width, wmask);
+    const uint32_t y0 = wrap_coord(f32_as_i32_sat(fly), height, hmask), y1 = wrap_coord(f32_as_i32_sat(ceilf(sy)), height, hmask);
     const f3 c00 = fetch(y0 * width + x0), c10 = fetch(y0 * width + x1);
     const f3 c01 = fetch(y1 * width + x0), c11 = fetch(y1 * width + x1);
     const f3 a = lerp3(c00, c10, fx), b = lerp3(c01, c11, fx);
@@ -62,9 +71,9 @@ RPT_D f3 sample_bilinear(const Fetch& fetch, uint32_t width, uint32_t height, fl
 
 struct Atlas {
     const uchar4* texels;
-    uint32_t width, height;
+    uint32_t width, height, wmask, hmask;  // masks: pow2_mask(size)
     RPT_D f3 sample(const float* rect, f2 uv) const {  // rect = (u0, v0, su, sv), kernels/src/bsdf.rs:356
-        return sample_bilinear(TexelRGBA8{texels}, width, height, rect[0] + uv.x * rect[2], rect[1] + uv.y * rect[3]);
+        return sample_bilinear(TexelRGBA8{texels}, width, height, wmask, hmask, rect[0] + uv.x * rect[2], rect[1] + uv.y * rect[3]);
     }
 };
 
@@ -273,14 +282,14 @@ RPT_D f3 scatter(f3 sundir, float sun_intensity, f3 origin, f3 direction) {  // 
 // are computed on the host (one value per config).
 struct SkyImage {
     const float4* texels;
-    uint32_t width, height;
+    uint32_t width, height, wmask, hmask;  // masks: pow2_mask(size)
     float yaw_sin, yaw_cos, intensity;  // intensity = sun.w * (1/15)
     RPT_D f3 lookup(f3 d) const {
         // Mat3::from_rotation_y(yaw) * d, columns (c,0,-s), (0,1,0), (s,0,c)
         const f3 r = mk3(yaw_cos * d.x + yaw_sin * d.z, d.y, -yaw_sin * d.x + yaw_cos * d.z);
         const float u = 0.5f + atan2f(r.z, r.x) / (2.0f * kPi);
         const float v = 1.0f - (0.5f + asinf(r.y) / kPi);
-        return sample_bilinear(TexelF32{texels}, width, height, u, v) * intensity;
+        return sample_bilinear(TexelF32{texels}, width, height, wmask, hmask, u, v) * intensity;
     }
 };
 

@@ -201,7 +201,7 @@ struct WideCursor {
         const f3 org_near = mk3(fmaf(adj.x, -1024.0f, org.x - apad.x), fmaf(adj.y, -1024.0f, org.y - apad.y), fmaf(adj.z, -1024.0f, org.z - apad.z));
         const f3 org_far = mk3(fmaf(adj.x, -1024.0f, org.x + apad.x), fmaf(adj.y, -1024.0f, org.y + apad.y), fmaf(adj.z, -1024.0f, org.z + apad.z));
 
-        const bool nx = ray.d.x < 0.0f, ny = ray.d.y < 0.0f, nz = ray.d.z < 0.0f;
+        const bool nx = (ray.oct_inv & 4u) == 0u, ny = (ray.oct_inv & 2u) == 0u, nz = (ray.oct_inv & 1u) == 0u;  // d.x < 0, ...
         // children 0..3 and 4..7: near/far byte words per axis depend on the ray's sign
         uint32_t h = test_four<0u>(s.half_1024_bytes, nx ? n3.z : n2.x, ny ? n4.x : n2.z, nz ? n4.z : n3.x, nx ? n2.x : n3.z, ny ? n2.z : n4.x, nz ? n3.x : n4.z, adj,
                                    org_near, org_far, best_t);

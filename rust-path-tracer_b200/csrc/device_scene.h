@@ -88,15 +88,19 @@ struct WaveState {
     float4* mis_a;   // last BSDF spectrum.xyz, bits(light record sampled by NEE)
     float4* mis_b;   // throughput before the last bounce .xyz, bits(wide triangle of that light)
     uint2* hit;      // bits(t), wide triangle | backface << 31
-    float4* sh_o;    // shadow queue: origin.xyz, max_t
+    float4* sh_o;    // shadow rays, indexed like q_hit: origin.xyz, max_t
     float4* sh_d;    //               direction.xyz, bits(slot)
     float4* sh_c;    //               contribution.xyz if unoccluded
     uint32_t* q_ext[2];
     uint32_t* q_hit;
     uint32_t* q_miss;
+    uint32_t* q_shaded;  // per hit: slot | kShadedNoNext | kShadedShadow (wf_shade_kernel -> wf_compact_shaded_kernel)
+    uint32_t* q_shadow;  // indices of the shadow rays to trace
     WaveCtl* ctl;
     unsigned long long* counters;  // [0] paths, [1] nearest rays, [2] any rays
 };
+
+constexpr uint32_t kShadedShadow = 0x80000000u, kShadedNoNext = 0x40000000u, kShadedSlotMask = 0x3FFFFFFFu;  // waves hold < 2^30 slots
 
 // Which pixel-samples a wave covers: slot = k * npix + j  ->  pixel = map(pix_base + j), sample k.
 struct WaveDesc {
@@ -109,6 +113,9 @@ struct WaveLaunch {
     cudaStream_t stream;
     int trace_blocks_per_sm;  // resident 128-thread blocks per SM of the trace kernels
     int refill_below;         // refill idle lanes once fewer than this many lanes of a warp hold a ray
+    bool pooled_triangles;    // wf_trace_coop_kernel (per-warp triangle pool) instead of wf_trace_kernel
+    uint32_t flush_at;        // test the pool once it holds this many pairs (<= 32) ...
+    int flush_waiting;        // ... or once this many lanes have nothing left to do but wait for it
 };
 
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole);
@@ -117,7 +124,8 @@ void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState
 void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState& s);
 void launch_wf_export_primary(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, const WaveDesc& d, uint32_t* ids);
 void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld& w, const WaveState& s, const WaveDesc& d, const uint2* rng,
-                     uint32_t bounce, int out_queue);
+                     uint32_t bounce);
+void launch_wf_compact_shaded(const WaveLaunch& l, const WaveState& s, int out_queue);
 void launch_wf_miss(const WaveLaunch& l, const FrameParams& f, const WaveState& s);
 void launch_wf_accumulate(const WaveLaunch& l, const WaveState& s, const WaveDesc& d, uint2* rng, float4* output);
 void launch_normalize(const float4* output, float* rgb, uint32_t npixels, float samples, cudaStream_t stream);

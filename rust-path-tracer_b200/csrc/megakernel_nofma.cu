@@ -22,7 +22,7 @@ struct MisState {  // what calculate_bsdf_mis_contribution reads from the previo
 __device__ f3 trace_path(const MegaParams& p, uint32_t px, uint32_t py, uint32_t key, unsigned long long* n_nearest,
                          unsigned long long* n_any, uint32_t* primary_id) {
     const Bvh2Scene bvh{p.nodes, p.triangles, p.vertices};
-    const Atlas atlas{p.atlas, p.atlas_w, p.atlas_h};
+    const Atlas atlas{p.atlas, p.atlas_w, p.atlas_h, pow2_mask(p.atlas_w), pow2_mask(p.atlas_h)};
     const uint32_t nee_mode = p.nee;
     const bool nee = nee_mode != RPT_NEE_NONE;
 

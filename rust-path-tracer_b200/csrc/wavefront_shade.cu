@@ -1,218 +1,173 @@
 // wavefront_shade.cu — the shading stages of the wavefront pipeline:
 //   shade       everything kernels/src/lib.rs:81-181 does at a surface hit: emission / MIS rules,
 //               attribute interpolation, normal map, PBR lobe sampling, the NEE light sample
-//               (queued as a shadow ray with its would-be contribution), throughput update,
+//               (stored as a shadow ray with its would-be contribution), throughput update,
 //               Russian roulette, and the next ray
 //   miss        procedural or HDR sky for escaped paths (lib.rs:66-79)
 //   accumulate  output[pixel] += (radiance, 1) per sample in sample order; rng.x += samples
 //               (lib.rs:225-226 / src/trace.rs:295-296)
 //   normalize   packed RGB framebuffer = output.xyz / samples (src/trace.rs:199-204)
 //
-// Materials (and small light tables) are staged in shared memory once per persistent block.
+// Materials are staged in shared memory once per persistent block.
 #include "device_scene.h"
 
 namespace rpt {
 
 constexpr int kShadeBlock = 256;
-constexpr int kShadeWarps = kShadeBlock / 32;
-constexpr uint32_t kSmemMaterials = 64;    // 6 KB
-constexpr uint32_t kSmemLightBins = 1024;  // 12 KB
+constexpr uint32_t kSmemMaterials = 64;  // 6 KB
 
 __device__ __forceinline__ uint32_t wave_pixel(const WaveDesc& d, uint32_t j) {
     const uint32_t i = d.pix_base + j;
     return d.pixel_map ? __ldg(d.pixel_map + i) : i;
 }
 
+// One thread per hit, no block-level synchronisation: what a hit produces is recorded in the word
+// q_shaded[i] = slot | kShadedNoNext | kShadedShadow (i = the hit's position in q_hit) and
+// wf_compact_shaded_kernel turns those words into the next extend queue and the shadow queue, in order.
+// The shadow ray itself is stored at index i (sh_o / sh_d / sh_c), the next ray in the path's own slot.
+template <bool MATS_IN_SMEM>
 __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f, WideWorld w, WaveState s, WaveDesc d, const uint2* __restrict__ rng,
-                                                               uint32_t bounce, int out_queue) {
-    __shared__ RptMaterialData sm_materials[kSmemMaterials];
-    __shared__ LightBin sm_bins[kSmemLightBins];
-    // queue appends are aggregated per block: warp ballots -> these counters -> one atomic pair per block
-    // and iteration (a single device counter sustains only a few atomics per nanosecond)
-    __shared__ uint32_t warp_shadow[kShadeWarps], warp_next[kShadeWarps], block_base[2];
-    const bool mats_in_smem = w.nmaterials <= kSmemMaterials;
-    const bool bins_in_smem = w.nbins > 0 && w.nbins <= kSmemLightBins;
-    if (mats_in_smem) {
+                                                               uint32_t bounce) {
+    __shared__ RptMaterialData sm_materials[MATS_IN_SMEM ? kSmemMaterials : 1];
+    if (MATS_IN_SMEM) {
         const uint32_t words = w.nmaterials * (uint32_t)(sizeof(RptMaterialData) / 4);
         for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(sm_materials)[i] = reinterpret_cast<const uint32_t*>(w.materials)[i];
+        __syncthreads();
     }
-    if (bins_in_smem) {
-        const uint32_t words = w.nbins * 3u;
-        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(sm_bins)[i] = reinterpret_cast<const uint32_t*>(w.light_bins)[i];
-    }
-    __syncthreads();
-    const RptMaterialData* materials = mats_in_smem ? sm_materials : w.materials;
-    const LightBin* bins = bins_in_smem ? sm_bins : w.light_bins;
-
     const uint32_t n = s.ctl->n_hit;
     const bool nee = f.nee != RPT_NEE_NONE;
     const bool last_bounce = bounce + 1u >= f.max_bounces;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {  // block-uniform trip count
-        const uint32_t i = base + threadIdx.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         bool want_shadow = false, want_next = false;
-        uint32_t slot = 0;
-        f3 sh_o{}, sh_d{}, sh_c{};
-        float sh_tmax = 0.0f;
-        f3 next_o{}, next_d{}, next_thr{};
-        float next_pdf = 0.0f;
-        uint32_t next_flags = 0;
+        const uint32_t slot = __ldg(s.q_hit + i);
+        const uint2 hr = s.hit[slot];
+        const float t = __uint_as_float(hr.x);
+        const uint32_t tri = hr.y & 0x7FFFFFFFu;
+        const bool backface = (hr.y >> 31) != 0u;
+        const float4 o4 = s.ray_o[slot], d4 = s.ray_d[slot], thr4 = s.thr[slot];
+        const f3 ro = xyz(o4), rd = xyz(d4);
+        const f3 throughput = xyz(thr4);
+        const uint32_t flags = __float_as_uint(d4.w);
+        const uint32_t last_lobe = (flags >> 8) & 1u;
+        const uint2 seed = __ldg(rng + wave_pixel(d, slot % d.npix));
+        Rng rstate{seed.x + slot / d.npix + seed.y, flags & 0xFFu};
 
-        if (i < n) {
-            slot = __ldg(s.q_hit + i);
-            const uint2 hr = s.hit[slot];
-            const float t = __uint_as_float(hr.x);
-            const uint32_t tri = hr.y & 0x7FFFFFFFu;
-            const bool backface = (hr.y >> 31) != 0u;
-            const float4 o4 = s.ray_o[slot], d4 = s.ray_d[slot], thr4 = s.thr[slot];
-            const f3 ro = xyz(o4), rd = xyz(d4);
-            f3 throughput = xyz(thr4);
-            const uint32_t flags = __float_as_uint(d4.w);
-            const uint32_t last_lobe = (flags >> 8) & 1u;
-            const uint2 seed = __ldg(rng + wave_pixel(d, slot % d.npix));
-            Rng rstate{seed.x + slot / d.npix + seed.y, flags & 0xFFu};
+        const float4* tp = w.bvh.tri_pos + 3u * (size_t)tri;
+        const float4 a4 = __ldg(tp), e14 = __ldg(tp + 1), e24 = __ldg(tp + 2);
+        const RptMaterialData& mat = MATS_IN_SMEM ? sm_materials[__float_as_uint(e14.w)] : w.materials[__float_as_uint(e14.w)];
+        const f3 emissive = mk3(mat.emissive[0], mat.emissive[1], mat.emissive[2]);
+        const f3 hit = ro + rd * t;
+        bool alive = true;
 
-            const float4* tp = w.bvh.tri_pos + 3u * (size_t)tri;
-            const float4 a4 = __ldg(tp), e14 = __ldg(tp + 1), e24 = __ldg(tp + 2);
-            const RptMaterialData& mat = materials[__float_as_uint(e14.w)];
-            const f3 emissive = mk3(mat.emissive[0], mat.emissive[1], mat.emissive[2]);
-            const f3 hit = ro + rd * t;
-            bool alive = true;
-
-            if (!zero3(emissive)) {  // lib.rs:86-109
-                if (backface) {
-                    alive = false;
-                } else if (!nee || bounce == 0u || last_lobe != kLobeDiffuse) {
-                    const f3 c = mask_nan(throughput * emissive);
-                    float4 r = s.rad[slot];
-                    r.x += c.x; r.y += c.y; r.z += c.z;
-                    s.rad[slot] = r;
-                    alive = false;
-                } else if (f.nee == RPT_NEE_MIS) {  // calculate_bsdf_mis_contribution, light_pick.rs:179-199
-                    const float4 ma = s.mis_a[slot], mb = s.mis_b[slot];
-                    f3 c = splat3(0.0f);
-                    if (tri == __float_as_uint(mb.w)) {
-                        const LightRecord& L = w.lights[__float_as_uint(ma.w)];
-                        const float lp = light_pdf(L.a_area.w, t, xyz(L.normal), rd);
-                        if (lp > 0.0f) {
-                            const float bsdf_pdf = thr4.w;
-                            const float wgt = power_heuristic(bsdf_pdf, lp);
-                            c = xyz(mb) * ((xyz(ma) * xyz(L.emission) * wgt / bsdf_pdf) / L.e1_pdf.w);
-                        }
+        if (!zero3(emissive)) {  // lib.rs:86-109
+            if (backface) {
+                alive = false;
+            } else if (!nee || bounce == 0u || last_lobe != kLobeDiffuse) {
+                const f3 c = mask_nan(throughput * emissive);
+                float4 r = s.rad[slot];
+                r.x += c.x; r.y += c.y; r.z += c.z;
+                s.rad[slot] = r;
+                alive = false;
+            } else if (f.nee == RPT_NEE_MIS) {  // calculate_bsdf_mis_contribution, light_pick.rs:179-199
+                const float4 ma = s.mis_a[slot], mb = s.mis_b[slot];
+                f3 c = splat3(0.0f);
+                if (tri == __float_as_uint(mb.w)) {
+                    const LightRecord& L = w.lights[__float_as_uint(ma.w)];
+                    const float lp = light_pdf(L.a_area.w, t, xyz(L.normal), rd);
+                    if (lp > 0.0f) {
+                        const float bsdf_pdf = thr4.w;
+                        const float wgt = power_heuristic(bsdf_pdf, lp);
+                        c = xyz(mb) * ((xyz(ma) * xyz(L.emission) * wgt / bsdf_pdf) / L.e1_pdf.w);
                     }
-                    c = mask_nan(c);
-                    float4 r = s.rad[slot];
-                    r.x += c.x; r.y += c.y; r.z += c.z;
-                    s.rad[slot] = r;
-                    alive = false;
                 }
-                // RPT_NEE_DIRECT after a diffuse bounce: fall through and shade the emitter as a surface
+                c = mask_nan(c);
+                float4 r = s.rad[slot];
+                r.x += c.x; r.y += c.y; r.z += c.z;
+                s.rad[slot] = r;
+                alive = false;
+            }
+            // RPT_NEE_DIRECT after a diffuse bounce: fall through and shade the emitter as a surface
+        }
+
+        if (alive) {
+            // lib.rs:111-129 — barycentrics re-derived from the hit point; normal not renormalised
+            const float4* sp = w.tri_shade + 4u * (size_t)tri;
+            const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2), s3 = __ldg(sp + 3);
+            const f3 bary = barycentric(hit, xyz(a4), xyz(e14), xyz(e24));
+            f3 normal = (bary.x * xyz(s0) + bary.y * xyz(s1)) + bary.z * xyz(s2);
+            f2 uv{(bary.x * s0.w + bary.y * s2.w) + bary.z * s3.y, (bary.x * s1.w + bary.y * s3.x) + bary.z * s3.z};
+            if (fminf(fmaxf(uv.x, 0.0f), 1.0f) != uv.x || fminf(fmaxf(uv.y, 0.0f), 1.0f) != uv.y) uv = f2{uv.x - floorf(uv.x), uv.y - floorf(uv.y)};
+            if (mat.has_normal_texture && w.tri_tangent) {  // lib.rs:131-141
+                const f3 nm = f.atlas.sample(mat.normals, uv) * 2.0f - splat3(1.0f);
+                const float4* tg = w.tri_tangent + 3u * (size_t)tri;
+                const f3 tangent = (bary.x * xyz(__ldg(tg)) + bary.y * xyz(__ldg(tg + 1))) + bary.z * xyz(__ldg(tg + 2));
+                const f3 bitangent = cross(tangent, normal);
+                normal = normalize((tangent * nm.x + bitangent * nm.y) + normal * nm.z);
             }
 
-            if (alive) {
-                // lib.rs:111-129 — barycentrics re-derived from the hit point; normal not renormalised
-                const float4* sp = w.tri_shade + 4u * (size_t)tri;
-                const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2), s3 = __ldg(sp + 3);
-                const f3 bary = barycentric(hit, xyz(a4), xyz(e14), xyz(e24));
-                f3 normal = (bary.x * xyz(s0) + bary.y * xyz(s1)) + bary.z * xyz(s2);
-                f2 uv{(bary.x * s0.w + bary.y * s2.w) + bary.z * s3.y, (bary.x * s1.w + bary.y * s3.x) + bary.z * s3.z};
-                if (fminf(fmaxf(uv.x, 0.0f), 1.0f) != uv.x || fminf(fmaxf(uv.y, 0.0f), 1.0f) != uv.y) uv = f2{uv.x - floorf(uv.x), uv.y - floorf(uv.y)};
-                if (mat.has_normal_texture && w.tri_tangent) {  // lib.rs:131-141
-                    const f3 nm = f.atlas.sample(mat.normals, uv) * 2.0f - splat3(1.0f);
-                    const float4* tg = w.tri_tangent + 3u * (size_t)tri;
-                    const f3 tangent = (bary.x * xyz(__ldg(tg)) + bary.y * xyz(__ldg(tg + 1))) + bary.z * xyz(__ldg(tg + 2));
-                    const f3 bitangent = cross(tangent, normal);
-                    normal = normalize((tangent * nm.x + bitangent * nm.y) + normal * nm.z);
-                }
+            const Pbr bsdf = make_pbr(mat, uv, f.atlas, f.clamp_lo, f.clamp_hi);
+            const f3 view = -rd;
+            const float r1 = rstate.next(), r2 = rstate.next(), r3 = rstate.next();
+            const BsdfSample bs = pbr_sample(bsdf, view, normal, mk3(r1, r2, r3));
 
-                const Pbr bsdf = make_pbr(mat, uv, f.atlas, f.clamp_lo, f.clamp_hi);
-                const f3 view = -rd;
-                const float r1 = rstate.next(), r2 = rstate.next(), r3 = rstate.next();
-                const BsdfSample bs = pbr_sample(bsdf, view, normal, mk3(r1, r2, r3));
-
-                uint32_t light_rec = 0, light_tri = 0;
-                if (nee && bs.lobe == kLobeDiffuse && w.nbins > 0u) {  // sample_direct_lighting, light_pick.rs:100-173
-                    const float l1 = rstate.next(), l2 = rstate.next();
-                    uint32_t bin_i = (uint32_t)fminf(l1 * (float)w.nbins, 4294967040.0f);
-                    bin_i = min(bin_i, w.nbins - 1u);  // l1 == 1.0 would index one past the end (CPU path panics)
-                    const LightBin bin = bins[bin_i];
-                    light_rec = l2 < bin.ratio ? bin.light_a : bin.light_b;
-                    const LightRecord& L = w.lights[light_rec];
-                    const float4 la = __ldg(&L.a_area), le1 = __ldg(&L.e1_pdf), le2 = __ldg(&L.e2_tri);
-                    light_tri = __float_as_uint(le2.w);
-                    const float q1 = rstate.next(), q2 = rstate.next();
-                    const float sq = sqrtf(q1);
-                    // (1-sq) a + sq(1-q2) b + sq q2 c  ==  a + sq(1-q2) e1 + sq q2 e2
-                    const f3 lp = xyz(la) + xyz(le1) * (sq * (1.0f - q2)) + xyz(le2) * (sq * q2);
-                    const f3 to_light = lp - hit;
-                    const float dist = length(to_light);
-                    const f3 l = to_light / dist;
-                    const float lpdf = light_pdf(la.w, dist, xyz(__ldg(&L.normal)), l);
-                    if (lpdf > 0.0f) {
-                        f3 fd;
-                        float bpdf;
-                        pbr_eval_diffuse(bsdf, view, normal, l, fd, bpdf);
-                        if (bpdf > 0.0f) {
-                            const float wgt = f.nee == RPT_NEE_MIS ? power_heuristic(lpdf, bpdf) : 1.0f;
-                            const f3 direct = (fd * xyz(__ldg(&L.emission)) * wgt / lpdf) / le1.w;
-                            const f3 c = throughput * direct;
-                            // a zero or non-finite contribution adds nothing whether or not the light is visible
-                            if (finite3(c) && !zero3(c)) {
-                                want_shadow = true;
-                                sh_o = hit + l * kEps;
-                                sh_d = l;
-                                sh_tmax = dist - kEps * 2.0f;
-                                sh_c = c;
-                            }
+            uint32_t light_rec = 0, light_tri = 0;
+            if (nee && bs.lobe == kLobeDiffuse && w.nbins > 0u) {  // sample_direct_lighting, light_pick.rs:100-173
+                const float l1 = rstate.next(), l2 = rstate.next();
+                uint32_t bin_i = (uint32_t)fminf(l1 * (float)w.nbins, 4294967040.0f);
+                bin_i = min(bin_i, w.nbins - 1u);  // l1 == 1.0 would index one past the end (CPU path panics)
+                const LightBin* bp = w.light_bins + bin_i;
+                const LightBin bin{__ldg(&bp->light_a), __ldg(&bp->light_b), __ldg(&bp->ratio)};
+                light_rec = l2 < bin.ratio ? bin.light_a : bin.light_b;
+                const LightRecord& L = w.lights[light_rec];
+                const float4 la = __ldg(&L.a_area), le1 = __ldg(&L.e1_pdf), le2 = __ldg(&L.e2_tri);
+                light_tri = __float_as_uint(le2.w);
+                const float q1 = rstate.next(), q2 = rstate.next();
+                const float sq = sqrtf(q1);
+                // (1-sq) a + sq(1-q2) b + sq q2 c  ==  a + sq(1-q2) e1 + sq q2 e2
+                const f3 lp = xyz(la) + xyz(le1) * (sq * (1.0f - q2)) + xyz(le2) * (sq * q2);
+                const f3 to_light = lp - hit;
+                const float dist = length(to_light);
+                const f3 l = to_light / dist;
+                const float lpdf = light_pdf(la.w, dist, xyz(__ldg(&L.normal)), l);
+                if (lpdf > 0.0f) {
+                    f3 fd;
+                    float bpdf;
+                    pbr_eval_diffuse(bsdf, view, normal, l, fd, bpdf);
+                    if (bpdf > 0.0f) {
+                        const float wgt = f.nee == RPT_NEE_MIS ? power_heuristic(lpdf, bpdf) : 1.0f;
+                        const f3 direct = (fd * xyz(__ldg(&L.emission)) * wgt / lpdf) / le1.w;
+                        const f3 c = throughput * direct;
+                        // a zero or non-finite contribution adds nothing whether or not the light is visible
+                        if (finite3(c) && !zero3(c)) {
+                            want_shadow = true;
+                            s.sh_o[i] = mk4(hit + l * kEps, dist - kEps * 2.0f);
+                            s.sh_d[i] = mk4(l, __uint_as_float(slot));
+                            s.sh_c[i] = mk4(c, 0.0f);
                         }
                     }
                 }
+            }
 
-                if (!last_bounce) {
-                    next_thr = throughput * (bs.spectrum / bs.pdf);
-                    next_d = bs.direction;
-                    next_o = hit + next_d * kEps;
-                    next_pdf = bs.pdf;
-                    want_next = true;
-                    if (bounce > f.min_bounces) {  // Russian roulette, lib.rs:175-181
-                        const float prob = max_element(next_thr);
-                        if (rstate.next() > prob) want_next = false;
-                        next_thr = next_thr * (1.0f / prob);
-                    }
-                    next_flags = (rstate.dim & 0xFFu) | (bs.lobe << 8);
-                    if (want_next && f.nee == RPT_NEE_MIS && bs.lobe == kLobeDiffuse) {
+            if (!last_bounce) {
+                f3 next_thr = throughput * (bs.spectrum / bs.pdf);
+                want_next = true;
+                if (bounce > f.min_bounces) {  // Russian roulette, lib.rs:175-181
+                    const float prob = max_element(next_thr);
+                    if (rstate.next() > prob) want_next = false;
+                    next_thr = next_thr * (1.0f / prob);
+                }
+                if (want_next) {
+                    s.ray_o[slot] = mk4(hit + bs.direction * kEps, 0.0f);
+                    s.ray_d[slot] = mk4(bs.direction, __uint_as_float((rstate.dim & 0xFFu) | (bs.lobe << 8)));
+                    s.thr[slot] = mk4(next_thr, bs.pdf);
+                    if (f.nee == RPT_NEE_MIS && bs.lobe == kLobeDiffuse) {
                         s.mis_a[slot] = mk4(bs.spectrum, __uint_as_float(light_rec));
                         s.mis_b[slot] = mk4(throughput, __uint_as_float(light_tri));
                     }
                 }
             }
         }
-        const uint32_t sh_mask = __ballot_sync(0xFFFFFFFFu, want_shadow), nx_mask = __ballot_sync(0xFFFFFFFFu, want_next);
-        if (lane == 0) { warp_shadow[warp] = (uint32_t)__popc(sh_mask); warp_next[warp] = (uint32_t)__popc(nx_mask); }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t ts = 0, tn = 0;
-            for (int w = 0; w < kShadeWarps; ++w) { const uint32_t a = warp_shadow[w], b = warp_next[w]; warp_shadow[w] = ts; warp_next[w] = tn; ts += a; tn += b; }
-            block_base[0] = ts ? atomicAdd(&s.ctl->n_shadow, ts) : 0u;
-            block_base[1] = tn ? atomicAdd(out_queue ? &s.ctl->n_ext[1] : &s.ctl->n_ext[0], tn) : 0u;
-        }
-        __syncthreads();
-        const uint32_t below = (1u << lane) - 1u;
-        if (want_shadow) {
-            const uint32_t q = block_base[0] + warp_shadow[warp] + (uint32_t)__popc(sh_mask & below);
-            s.sh_o[q] = mk4(sh_o, sh_tmax);
-            s.sh_d[q] = mk4(sh_d, __uint_as_float(slot));
-            s.sh_c[q] = mk4(sh_c, 0.0f);
-        }
-        if (want_next) {
-            const uint32_t q = block_base[1] + warp_next[warp] + (uint32_t)__popc(nx_mask & below);
-            (out_queue ? s.q_ext[1] : s.q_ext[0])[q] = slot;
-            s.ray_o[slot] = mk4(next_o, 0.0f);
-            s.ray_d[slot] = mk4(next_d, __uint_as_float(next_flags));
-            s.thr[slot] = mk4(next_thr, next_pdf);
-        }
-        __syncthreads();  // the shared counters are rewritten next iteration
+        s.q_shaded[i] = slot | (want_next ? 0u : kShadedNoNext) | (want_shadow ? kShadedShadow : 0u);
     }
 }
 
@@ -265,8 +220,9 @@ __global__ void normalize_kernel(const float4* __restrict__ output, float* __res
 }
 
 void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld& w, const WaveState& s, const WaveDesc& d, const uint2* rng,
-                     uint32_t bounce, int out_queue) {
-    wf_shade_kernel<<<l.grid * 4, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce, out_queue);
+                     uint32_t bounce) {
+    if (w.nmaterials <= kSmemMaterials) wf_shade_kernel<true><<<l.grid * 4, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce);
+    else wf_shade_kernel<false><<<l.grid * 4, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce);
 }
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole) { wf_reset_kernel<<<1, 32, 0, l.stream>>>(s, next_queue, whole); }
 void launch_wf_miss(const WaveLaunch& l, const FrameParams& f, const WaveState& s) {

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kTraceBlock, 8) wf_trace_kernel(WideScene bvh,
 
     SmemStack st{&slabs[warp][0][lane], 0, perm_table};
     WideCursor<NEAREST> c;
-    uint32_t item = 0;       // path slot (NEAREST) / shadow-queue index (ANY)
+    uint32_t item = 0;       // path slot (NEAREST) / index of the shadow ray (ANY)
     bool busy = false;       // this lane holds an unfinished ray
     bool exhausted = false;  // the cursor ran past the end of the queue (warp-uniform)
 
@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(kTraceBlock, 8) wf_trace_kernel(WideScene bvh,
                         o = s.ray_o[item];
                         dv = s.ray_d[item];
                     } else {
-                        item = i;
-                        o = s.sh_o[i];
-                        dv = s.sh_d[i];
+                        item = __ldg(s.q_shadow + i);
+                        o = s.sh_o[item];
+                        dv = s.sh_d[item];
                         max_t = o.w;
                     }
                     c.begin(xyz(o), xyz(dv), max_t);
@@ -157,38 +157,279 @@ __global__ void __launch_bounds__(kTraceBlock, 8) wf_trace_kernel(WideScene bvh,
     }
 }
 
-// Ballot/popc stream compaction of the traced slots into the hit and miss queues, in input order.
-// Counts are aggregated per block (warp ballots -> shared memory -> ONE atomic pair per block and
-// iteration), because a single counter only sustains a few atomics per nanosecond.
-__global__ void __launch_bounds__(256) wf_compact_kernel(WaveState s, int in_queue, bool identity, uint32_t n_identity) {
-    __shared__ uint32_t warp_hits[8], warp_misses[8], block_base[2];
+// ---- cooperative variant: ray/triangle tests are pooled per warp -------------------------------
+// In the kernel above a lane that reaches triangles tests them itself while the other lanes of the warp wait:
+// on incoherent bounces that loop runs with ~3 of 32 lanes enabled and costs as many issue slots as all the
+// node visits (ncu, profiles/).  Here every round is warp-converged: lanes with pending child nodes visit one
+// node; the triangles they hit are appended as (owner lane, triangle) pairs to a per-warp ring in shared
+// memory (two ballots give every lane its offset); whenever the ring holds a full warp's worth — or lanes are
+// only waiting for it — all 32 lanes take one pair each, read the owner's ray from a shared slab, run the exact
+// ray/triangle test and merge the result with a 64-bit atomicMin on (t bits, triangle, back-face) in the
+// owner's result slot.  A lane's culling bound is refreshed from its slot after every test pass, so deferring a
+// test only ever makes traversal visit more nodes, never fewer; equal-t ties go to the lower wide triangle
+// index whatever the scheduling (deterministic).  A ray is finished when its stack is empty and none of its
+// pairs is queued.
+constexpr uint32_t kPoolCapacity = 128;   // < 32 pairs carried over + at most 3 per lane and round
+constexpr uint32_t kPoolOwnerShift = 27;  // pair = owner lane << 27 | wide triangle index (rpt_upload_world checks the range)
+
+template <bool NEAREST>
+__global__ void __launch_bounds__(kTraceBlock, 8) wf_trace_coop_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
+                                                                       int refill_below, uint32_t flush_at, int flush_waiting) {
+    __shared__ uint2 slabs[kTraceWarps][kWideStackCapacity][32];
+    __shared__ float4 ray_slab[kTraceWarps][2][32];  // [0]: origin.xyz  [1]: direction.xyz, max_t
+    __shared__ unsigned long long best_slab[kTraceWarps][32];
+    __shared__ uint32_t pool_slab[kTraceWarps][kPoolCapacity];
+    __shared__ uint8_t perm_table[8 * 256];
+    for (uint32_t i = threadIdx.x; i < 8u * 256u; i += kTraceBlock) perm_table[i] = (uint8_t)octant_permute(i >> 8, i & 0xFFu);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lanes_below = (1u << lane) - 1u;
+    const uint32_t n = NEAREST ? (identity ? n_identity : (in_queue ? s.ctl->n_ext[1] : s.ctl->n_ext[0])) : s.ctl->n_shadow;
+    const uint32_t* __restrict__ queue = in_queue ? s.q_ext[1] : s.q_ext[0];
+    uint32_t* fetch = NEAREST ? &s.ctl->fetch_extend : &s.ctl->fetch_shadow;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.counters + (NEAREST ? 1 : 2), (unsigned long long)n);
+
+    float4* const ray_o = ray_slab[warp][0];
+    float4* const ray_d = ray_slab[warp][1];
+    unsigned long long* const best = best_slab[warp];
+    uint32_t* const pool = pool_slab[warp];
+    // "no hit yet": nearest accepts t < 1e6 (intersection.rs:68,195), i.e. keys below bits(1e6) << 32
+    const unsigned long long kNoHit = NEAREST ? ((unsigned long long)__float_as_uint(1000000.0f) << 32) : ~0ull;
+
+    SmemStack st{&slabs[warp][0][lane], 0, perm_table};
+    WideCursor<NEAREST> c;
+    c.ngroup = make_uint2(0u, 0u);
+    uint32_t item = 0;       // path slot (NEAREST) / shadow-queue index (ANY)
+    uint32_t tris = 0;       // triangle hits of this lane's last node visit not yet in the pool
+    bool busy = false;       // this lane holds an unfinished ray
+    bool exhausted = false;  // the cursor ran past the end of the queue (warp-uniform)
+    bool tested = false;     // a test pass ran since the lanes last read their result slots (warp-uniform)
+    uint32_t count = 0;      // pairs in the ring (warp-uniform)
+    uint32_t head_seq = 0;   // pairs tested so far; pair number q sits in pool[q % kPoolCapacity] (warp-uniform)
+    uint32_t last_seq = 0;   // number after this lane's newest pair: all of its pairs are tested once head_seq reaches it
+
+    // All 32 lanes: test the first min(count, 32) pairs of the ring.
+    auto test_pool = [&]() {
+        const uint32_t take = min(count, 32u);
+        if (lane < take) {
+            const uint32_t pair = pool[(head_seq + lane) % kPoolCapacity];
+            const uint32_t owner = pair >> kPoolOwnerShift, ti = pair & ((1u << kPoolOwnerShift) - 1u);
+            const float4* rec = bvh.tri_pos + 3u * (size_t)ti;
+            const float4 a = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
+            const float4 o = ray_o[owner], d = ray_d[owner];
+            float t;
+            bool back;
+            if (ray_triangle(xyz(o), xyz(d), xyz(a), xyz(e1), xyz(e2), t, back) && t > 0.001f && (NEAREST || (t <= d.w && t < 1000000.0f))) {
+                const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (ti << 1) | (back ? 1u : 0u);
+                if (key < best[owner]) atomicMin(best + owner, key);
+            }
+        }
+        count -= take;
+        head_seq += take;
+        tested = true;
+        __syncwarp();
+    };
+
+    for (;;) {
+        // ---- refill idle lanes ---------------------------------------------------------------------
+        if (!exhausted) {
+            const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !busy);
+            if (idle) {
+                const int leader = __ffs((int)idle) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                const uint32_t i = base + (uint32_t)__popc(idle & lanes_below);
+                exhausted = base + (uint32_t)__popc(idle) >= n;
+                if (!busy && i < n) {
+                    float4 o, dv;
+                    float max_t = 0.0f;
+                    if (NEAREST) {
+                        item = identity ? i : __ldg(queue + i);
+                        o = s.ray_o[item];
+                        dv = s.ray_d[item];
+                    } else {
+                        item = __ldg(s.q_shadow + i);
+                        o = s.sh_o[item];
+                        dv = s.sh_d[item];
+                        max_t = o.w;
+                    }
+                    c.begin(xyz(o), xyz(dv), max_t);
+                    st.n = 0;
+                    busy = true;
+                    ray_o[lane] = o;
+                    ray_d[lane] = make_float4(dv.x, dv.y, dv.z, max_t);
+                    best[lane] = kNoHit;
+                    last_seq = head_seq;
+                }
+                __syncwarp();
+            }
+        }
+        uint32_t live = __ballot_sync(0xFFFFFFFFu, busy);
+        if (live == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- warp-converged rounds -----------------------------------------------------------------
+        for (;;) {
+            if (tested) {  // results moved: tighten the culling bound / stop an occluded shadow ray
+                tested = false;
+                if (busy) {
+                    const unsigned long long key = best[lane];
+                    if (NEAREST) c.best_t = fminf(c.best_t, __uint_as_float((uint32_t)(key >> 32)));
+                    else if (key != kNoHit) { c.ngroup.y = 0u; st.n = 0; tris = 0u; }  // queued pairs still have to drain
+                }
+            }
+            if (busy && tris == 0u && c.has_nodes()) {
+                c.visit_node(bvh, st);
+                tris = c.tgroup.y;
+                c.advance(st);
+            }
+            // append up to three of this lane's triangle hits to the ring; two ballots place every lane
+            {
+                const uint32_t mine = min((uint32_t)__popc(tris), 3u);
+                const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, (mine & 1u) != 0u), b1 = __ballot_sync(0xFFFFFFFFu, (mine & 2u) != 0u);
+                if ((b0 | b1) != 0u) {
+                    if (mine != 0u) {
+                        uint32_t q = head_seq + count + (uint32_t)__popc(b0 & lanes_below) + 2u * (uint32_t)__popc(b1 & lanes_below);
+                        const uint32_t tag = lane << kPoolOwnerShift;
+                        last_seq = q + mine;
+                        for (uint32_t j = 0; j < mine; ++j, ++q) {
+                            const int k = highest_bit(tris);
+                            tris &= ~(1u << k);
+                            pool[q % kPoolCapacity] = tag | (c.tgroup.x + (uint32_t)__popc(c.tvalid & ~(0xFFFFFFFFu << k)));
+                        }
+                    }
+                    count += (uint32_t)__popc(b0) + 2u * (uint32_t)__popc(b1);
+                    __syncwarp();
+                    while (count >= 32u) test_pool();
+                }
+            }
+            const uint32_t through = __ballot_sync(0xFFFFFFFFu, busy && tris == 0u && !c.has_nodes());  // nothing left to traverse
+            uint32_t waiting = __ballot_sync(0xFFFFFFFFu, busy && tris == 0u && !c.has_nodes() && (int)(head_seq - last_seq) < 0);
+            if (count != 0u && (count >= flush_at || __popc(waiting) >= flush_waiting || through == live)) {
+                while (count != 0u) test_pool();
+                waiting = 0u;
+            }
+            const uint32_t done = through & ~waiting;
+            if ((done >> lane) & 1u) {
+                busy = false;
+                const unsigned long long key = best[lane];
+                if (NEAREST) {  // every traced slot gets a record; kMissRecord marks "no hit" for wf_compact_kernel
+                    s.hit[item] = key != kNoHit ? make_uint2((uint32_t)(key >> 32), ((uint32_t)key >> 1) | ((uint32_t)key << 31)) : make_uint2(0u, kMissRecord);
+                } else if (key == kNoHit) {  // unoccluded: radiance += mask_nan(contribution) (lib.rs:164; masked when queued)
+                    const uint32_t slot = __float_as_uint(s.sh_d[item].w);
+                    const float4 add = s.sh_c[item];
+                    float4 r = s.rad[slot];
+                    r.x += add.x; r.y += add.y; r.z += add.z;
+                    s.rad[slot] = r;
+                }
+            }
+            live &= ~done;
+            if (live == 0u || (!exhausted && __popc(live) < refill_below)) break;
+        }
+    }
+}
+
+// ---- order-preserving two-way stream compaction ------------------------------------------------
+// Both compaction kernels split one input stream into two output queues IN INPUT ORDER (the shading stages
+// then read path state coalesced although rays finish in any order).  A block handles kCompactItems
+// consecutive items per thread; the per-thread counts of both outputs ride in one word through a warp
+// shuffle scan and a warp-total scan in shared memory, and the block reserves its two output ranges with ONE
+// atomic pair (a single device counter only sustains a few atomics per nanosecond).
+constexpr int kCompactBlock = 256;
+constexpr int kCompactItems = 4;
+constexpr uint32_t kCompactTile = kCompactBlock * kCompactItems;
+
+// `mine` = (count for queue B) << 16 | (count for queue A) of this thread; returns this thread's first output
+// index in both queues, packed the same way relative to the block's reservations base_a / base_b.
+__device__ __forceinline__ void compact_reserve(uint32_t mine, uint32_t* count_a, uint32_t* count_b, uint32_t& out_a, uint32_t& out_b) {
+    __shared__ uint32_t warp_total[kCompactBlock / 32], block_base[2];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += up;
+    }
+    if (lane == 31u) warp_total[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t wt = lane < kCompactBlock / 32 ? warp_total[lane] : 0u;
+        uint32_t wincl = wt;
+#pragma unroll
+        for (int d = 1; d < kCompactBlock / 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, wincl, d);
+            if ((int)lane >= d) wincl += up;
+        }
+        if (lane < kCompactBlock / 32) warp_total[lane] = wincl - wt;  // exclusive
+        if (lane == kCompactBlock / 32 - 1) {
+            const uint32_t ta = wincl & 0xFFFFu, tb = wincl >> 16;
+            block_base[0] = ta ? atomicAdd(count_a, ta) : 0u;
+            block_base[1] = tb ? atomicAdd(count_b, tb) : 0u;
+        }
+    }
+    __syncthreads();
+    const uint32_t excl = warp_total[warp] + incl - mine;
+    out_a = block_base[0] + (excl & 0xFFFFu);
+    out_b = block_base[1] + (excl >> 16);
+    __syncthreads();  // the shared words are rewritten by the next tile
+}
+
+// After extend: the traced slots go to q_hit or q_miss; counts the rays actually traced.
+__global__ void __launch_bounds__(kCompactBlock) wf_compact_kernel(WaveState s, int in_queue, bool identity, uint32_t n_identity) {
     const uint32_t n = identity ? n_identity : (in_queue ? s.ctl->n_ext[1] : s.ctl->n_ext[0]);
     const uint32_t* __restrict__ queue = in_queue ? s.q_ext[1] : s.q_ext[0];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {  // block-uniform trip count
-        const uint32_t i = base + threadIdx.x;
-        const bool active = i < n;
-        uint32_t slot = 0;
-        bool hit = false;
-        if (active) {
-            slot = identity ? i : __ldg(queue + i);
-            hit = s.hit[slot].y != kMissRecord;
+    for (uint32_t tile = blockIdx.x * kCompactTile; tile < n; tile += gridDim.x * kCompactTile) {  // block-uniform trip count
+        const uint32_t first = tile + threadIdx.x * kCompactItems;
+        uint32_t slot[kCompactItems];
+        uint32_t hit_bits = 0, valid_bits = 0;
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) {
+            const uint32_t i = first + k;
+            slot[k] = 0;
+            if (i < n) {
+                slot[k] = identity ? i : __ldg(queue + i);
+                valid_bits |= 1u << k;
+                if (s.hit[slot[k]].y != kMissRecord) hit_bits |= 1u << k;
+            }
         }
-        const uint32_t hmask = __ballot_sync(0xFFFFFFFFu, active && hit), mmask = __ballot_sync(0xFFFFFFFFu, active && !hit);
-        if (lane == 0) { warp_hits[warp] = (uint32_t)__popc(hmask); warp_misses[warp] = (uint32_t)__popc(mmask); }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t th = 0, tm = 0;
-            for (int w = 0; w < 8; ++w) { const uint32_t h = warp_hits[w], m = warp_misses[w]; warp_hits[w] = th; warp_misses[w] = tm; th += h; tm += m; }
-            block_base[0] = th ? atomicAdd(&s.ctl->n_hit, th) : 0u;
-            block_base[1] = tm ? atomicAdd(&s.ctl->n_miss, tm) : 0u;
+        const uint32_t miss_bits = valid_bits & ~hit_bits;
+        uint32_t out_hit, out_miss;
+        compact_reserve((uint32_t)__popc(hit_bits) | ((uint32_t)__popc(miss_bits) << 16), &s.ctl->n_hit, &s.ctl->n_miss, out_hit, out_miss);
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) {
+            if ((hit_bits >> k) & 1u) s.q_hit[out_hit++] = slot[k];
+            if ((miss_bits >> k) & 1u) s.q_miss[out_miss++] = slot[k];
         }
-        __syncthreads();
-        const uint32_t below = (1u << lane) - 1u;
-        if (active && hit) s.q_hit[block_base[0] + warp_hits[warp] + (uint32_t)__popc(hmask & below)] = slot;
-        if (active && !hit) s.q_miss[block_base[1] + warp_misses[warp] + (uint32_t)__popc(mmask & below)] = slot;
-        __syncthreads();  // block_base / warp_* are rewritten next iteration
+    }
+}
+
+// After shade: q_shaded[i] = slot | flags for every hit i.  Paths that go on are queued for the next extend
+// pass (their slot), hits that sampled a light are queued for shadow-connect (the index i of their shadow ray).
+__global__ void __launch_bounds__(kCompactBlock) wf_compact_shaded_kernel(WaveState s, int out_queue) {
+    const uint32_t n = s.ctl->n_hit;
+    uint32_t* __restrict__ q_next = out_queue ? s.q_ext[1] : s.q_ext[0];
+    uint32_t* count_next = out_queue ? &s.ctl->n_ext[1] : &s.ctl->n_ext[0];
+    for (uint32_t tile = blockIdx.x * kCompactTile; tile < n; tile += gridDim.x * kCompactTile) {
+        const uint32_t first = tile + threadIdx.x * kCompactItems;
+        uint32_t word[kCompactItems];
+        uint32_t next_bits = 0, shadow_bits = 0;
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) {
+            const uint32_t i = first + k;
+            word[k] = i < n ? s.q_shaded[i] : kShadedNoNext;
+            if (!(word[k] & kShadedNoNext)) next_bits |= 1u << k;
+            if (word[k] & kShadedShadow) shadow_bits |= 1u << k;
+        }
+        uint32_t out_next, out_shadow;
+        compact_reserve((uint32_t)__popc(next_bits) | ((uint32_t)__popc(shadow_bits) << 16), count_next, &s.ctl->n_shadow, out_next, out_shadow);
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) {
+            if ((next_bits >> k) & 1u) q_next[out_next++] = word[k] & kShadedSlotMask;
+            if ((shadow_bits >> k) & 1u) s.q_shadow[out_shadow++] = first + k;
+        }
     }
 }
 
@@ -211,11 +452,21 @@ void launch_wf_generate(const WaveLaunch& l, const FrameParams& f, const WaveSta
     wf_generate_kernel<<<l.grid * 2, 256, 0, l.stream>>>(f, s, d, rng);
 }
 void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, int in_queue, bool identity_queue, uint32_t n_identity) {
-    wf_trace_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below);
-    wf_compact_kernel<<<l.grid * 4, 256, 0, l.stream>>>(s, in_queue, identity_queue, n_identity);
+    if (l.pooled_triangles)
+        wf_trace_coop_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below,
+                                                                                                 l.flush_at, l.flush_waiting);
+    else
+        wf_trace_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below);
+    wf_compact_kernel<<<l.grid * 2, kCompactBlock, 0, l.stream>>>(s, in_queue, identity_queue, n_identity);
+}
+void launch_wf_compact_shaded(const WaveLaunch& l, const WaveState& s, int out_queue) {
+    wf_compact_shaded_kernel<<<l.grid * 2, kCompactBlock, 0, l.stream>>>(s, out_queue);
 }
 void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState& s) {
-    wf_trace_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below);
+    if (l.pooled_triangles)
+        wf_trace_coop_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.flush_at, l.flush_waiting);
+    else
+        wf_trace_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below);
 }
 void launch_wf_export_primary(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, const WaveDesc& d, uint32_t* ids) {
     wf_export_primary_kernel<<<(d.npix + 255) / 256, 256, 0, l.stream>>>(bvh, s, d, ids);

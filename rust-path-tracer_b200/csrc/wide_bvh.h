@@ -48,6 +48,6 @@ struct WideBvh {
 bool build_wide_bvh(const RptBVHNode* nodes, uint32_t nnodes, const uint32_t* triangles, uint32_t ntriangles,
                     const RptPerVertexData* vertices, uint32_t nvertices, WideBvh& out, const char** error);
 
-constexpr uint32_t kWideStackCapacity = 24;
+constexpr uint32_t kWideStackCapacity = 16;  // 8-wide: a 1M-triangle scene is 10 levels deep; deeper trees are rejected at upload
 
 }  // namespace rpt
