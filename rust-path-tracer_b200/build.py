@@ -66,7 +66,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OUT_DIR, os.path.basename(src) + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
+            # *_nofma.cu: the id-critical arithmetic (exact.cuh) — no FMA contraction, IEEE division and sqrt.
+            # wavefront_shade.cu: shading is held to a radiance tolerance, not to bit identity, so division and
+            # sqrt use the 2-ulp approximate forms (no special-case subroutine: ncu showed a third of the
+            # kernel's instructions inside it); transcendentals stay the accurate ones.
             extra = ["-fmad=false"] if src.endswith("_nofma.cu") else []
+            if os.path.basename(src) == "wavefront_shade.cu":
+                extra += ["-prec-div=false", "-prec-sqrt=false"]
             cmd = [nvcc, *ARCH_FLAGS, *NVCC_FLAGS, *extra, "-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-x", "cu", "-c", src, "-o", obj]
             jobs.append((src, cmd))
 
