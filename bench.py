@@ -337,8 +337,9 @@ def run_b200(args):
                                     "unit": "Mpaths/s", "mrays_per_s": (c2["nearest_rays"] + c2["any_rays"]) / ms2 / 1e3}}
 
     # ---- end to end through the C ABI with host buffers: H2D seeds + config, enqueue, D2H frame --
-    fb = np.empty(npix * 3, np.float32)
-    step_seeds = seeds.copy()
+    fb = capi.pinned_empty(npix * 3, np.float32)  # page-locked host buffers (rpt_host_alloc)
+    step_seeds = capi.pinned_empty(seeds.shape, np.uint32)
+    step_seeds[...] = seeds
     r.write_output(None)
     barrier()
     t0 = time.perf_counter()
@@ -354,7 +355,7 @@ def run_b200(args):
         dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     line["e2e"] = {"value": npix * spp * args.steps * world_size / float(e2e[0]) / 1e6, "unit": "Mpaths/s",
                    "h2d_bytes_per_step": 80 + 8 * npix, "d2h_bytes_per_step": 12 * npix,
-                   "what": "per step: rpt_set_config + rpt_write_rng (host seeds) + rpt_enqueue + rpt_read_framebuffer (host RGB)"}
+                   "what": "per step: rpt_set_config + rpt_write_rng (pinned host seeds) + rpt_enqueue + rpt_read_framebuffer (pinned host RGB)"}
     if not np.isfinite(fb).all():
         line["e2e"]["nan_pixels"] = int((~np.isfinite(fb.reshape(-1, 3)).all(axis=1)).sum())
 

@@ -87,6 +87,14 @@ int rpt_write_output(rpt_context* ctx, const float* rgba, size_t npixels);
  * 32x32 tile index t satisfies t % tile_count == tile_rank; other pixels stay untouched. */
 int rpt_set_tile_partition(rpt_context* ctx, uint32_t tile_rank, uint32_t tile_count);
 
+/* ---- host staging memory --------------------------------------------------------------- */
+/* Page-locked host memory for the buffers that cross the boundary every batch (seeds in, frame out):
+ * the counterpart of gpgpu-rs's mapped staging buffers behind GpuBuffer::write / read_blocking
+ * (src/trace.rs:198,219-221).  Any host pointer is accepted by the calls above and below; buffers from
+ * rpt_host_alloc are copied at full PCIe/C2C rate instead of through the driver's bounce buffer. */
+int rpt_host_alloc(size_t bytes, void** out_ptr);
+int rpt_host_free(void* ptr);
+
 /* ---- run ------------------------------------------------------------------------------- */
 int rpt_enqueue(rpt_context* ctx, uint32_t n_samples); /* asynchronous */
 int rpt_sync(rpt_context* ctx);                        /* FW.poll_blocking() */

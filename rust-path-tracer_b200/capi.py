@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -26,7 +27,7 @@ DEVICE_SYMBOLS = [
     "rpt_set_config", "rpt_write_rng", "rpt_read_rng", "rpt_write_output", "rpt_set_tile_partition", "rpt_enqueue",
     "rpt_sync", "rpt_read_output", "rpt_read_framebuffer", "rpt_read_primary_ids", "rpt_get_counters",
     "rpt_reset_counters", "rpt_get_device_ms", "rpt_set_stage_timing", "rpt_get_stage_timing", "rpt_comm_unique_id", "rpt_comm_init", "rpt_comm_reduce_output",
-    "rpt_comm_destroy",
+    "rpt_comm_destroy", "rpt_host_alloc", "rpt_host_free",
 ]
 
 
@@ -111,6 +112,37 @@ def lib() -> C.CDLL:
             if name != "rpt_last_error":
                 fn.restype = C.c_int
     return _lib
+
+
+class _PinnedBlock:
+    """Owner of one rpt_host_alloc block; freed when the last numpy view of it is collected."""
+
+    def __init__(self, nbytes: int):
+        self.address = C.c_void_p()
+        check(lib().rpt_host_alloc(C.c_size_t(nbytes), C.byref(self.address)), "rpt_host_alloc")
+        self.buffer = (C.c_uint8 * nbytes).from_address(self.address.value)
+
+    def __del__(self):
+        try:
+            if self.address:
+                lib().rpt_host_free(self.address)
+                self.address = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """An uninitialised numpy array in page-locked host memory (rpt_host_alloc); needs a CUDA device."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    block = _PinnedBlock(max(1, count * dtype.itemsize))
+    arr = np.frombuffer(block.buffer, dtype=dtype, count=count).reshape(shape)
+    _PINNED_OWNERS[arr.ctypes.data] = block  # numpy keeps `block.buffer` alive, not `block`; tie their lifetimes
+    weakref.finalize(arr, _PINNED_OWNERS.pop, arr.ctypes.data, None)
+    return arr
+
+
+_PINNED_OWNERS: dict = {}
 
 
 def ptr(a: np.ndarray | None):

@@ -99,9 +99,6 @@ struct rpt_context {
     // trace-kernel tunables (defaults chosen on B200; RPT_* env vars override for sweeps)
     int trace_blocks_per_sm = 8;
     int refill_below = 20;
-    bool pooled_triangles = false;
-    uint32_t flush_at = 32;
-    int flush_waiting = 8;
 
     // scene, reference layouts (megakernel arm)
     DevBuf<RptPerVertexData> d_vertices;
@@ -319,7 +316,7 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
     const FrameParams f = frame_params(c);
     const WideWorld w = wide_world(c);
     const WaveState s = wave_state(c);
-    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below, c->pooled_triangles, c->flush_at, c->flush_waiting};
+    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below};
     const uint32_t nslots = d.npix * d.k_samples;
     c->launch(RPT_STAGE_OTHER, [&] { launch_wf_reset(l, s, 1, true); });
     c->launch(RPT_STAGE_GENERATE, [&] { launch_wf_generate(l, f, s, d, c->d_rng.p); });
@@ -399,9 +396,6 @@ extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
     c->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("RPT_TRACE_BLOCKS_PER_SM")) c->trace_blocks_per_sm = std::max(1, atoi(v));
     if (const char* v = getenv("RPT_REFILL_BELOW")) c->refill_below = atoi(v);
-    if (const char* v = getenv("RPT_POOLED_TRIANGLES")) c->pooled_triangles = atoi(v) != 0;
-    if (const char* v = getenv("RPT_FLUSH_AT")) c->flush_at = (uint32_t)std::min(32, std::max(1, atoi(v)));
-    if (const char* v = getenv("RPT_FLUSH_WAITING")) c->flush_waiting = std::max(1, atoi(v));
     if (const char* v = getenv("RPT_WAVE_SLOTS")) c->wave_slots = (uint32_t)std::max(1024, atoi(v));
     *out_ctx = c;
     return RPT_OK;
@@ -450,7 +444,7 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
     if (!vertices || !triangles || !nodes || !materials || !lights || nvertices == 0 || ntriangles == 0 || nnodes == 0 || nmaterials == 0 || nlights == 0)
         return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: null or empty buffer");
-    if (ntriangles >= (1u << 27)) return c->fail(RPT_ERR_UNSUPPORTED, "more than 2^27 triangles (the trace kernel packs lane and triangle in one word)");
+    if (ntriangles >= 0x80000000u) return c->fail(RPT_ERR_UNSUPPORTED, "more than 2^31 triangles");
     if ((atlas_rgba8 && (atlas_w == 0 || atlas_h == 0)) || (sky_rgba32f && (sky_w == 0 || sky_h == 0)))
         return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: image with a zero dimension");
     for (size_t t = 0; t < (size_t)ntriangles; ++t)
@@ -647,6 +641,32 @@ extern "C" int rpt_set_tile_partition(rpt_context* c, uint32_t tile_rank, uint32
     c->tile_rank = tile_rank;
     c->tile_count = tile_count;
     return rebuild_pixel_map(c);
+}
+
+// ============================================================================ host staging memory
+extern "C" int rpt_host_alloc(size_t bytes, void** out_ptr) {
+    if (!out_ptr) return RPT_ERR_INVALID_ARGUMENT;
+    *out_ptr = nullptr;
+    if (bytes == 0) return RPT_ERR_INVALID_ARGUMENT;
+    const cudaError_t e = cudaHostAlloc(out_ptr, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        *out_ptr = nullptr;
+        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? RPT_ERR_NO_DEVICE : RPT_ERR_CUDA;
+    }
+    return RPT_OK;
+}
+
+extern "C" int rpt_host_free(void* ptr) {
+    if (!ptr) return RPT_ERR_INVALID_ARGUMENT;
+    const cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaFreeHost: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return RPT_ERR_CUDA;
+    }
+    return RPT_OK;
 }
 
 // ============================================================================ run

@@ -24,11 +24,13 @@ namespace rpt {
 
 #if defined(__CUDACC__)
 RPT_D int highest_bit(uint32_t v) { return 31 - __clz((int)v); }
+RPT_D void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 RPT_D int popcount(uint32_t v) { return __popc(v); }
 RPT_D float as_float(uint32_t v) { return __uint_as_float(v); }
 RPT_D uint32_t as_uint(float v) { return __float_as_uint(v); }
 #else
 inline int highest_bit(uint32_t v) { return 31 - __builtin_clz(v); }
+inline void prefetch_l1(const void*) {}
 inline int popcount(uint32_t v) { return __builtin_popcount(v); }
 inline float as_float(uint32_t v) { float f; memcpy(&f, &v, 4); return f; }
 inline uint32_t as_uint(float v) { uint32_t u; memcpy(&u, &v, 4); return u; }
@@ -67,7 +69,6 @@ RPT_HD uint32_t octant_permute(uint32_t oct, uint32_t m) {
 struct WideRay {
     f3 o, d;
     f3 idir;        // 1 / d with |d| clamped away from 0
-    f3 pad_scale;   // |idir| * 2^-21: conservative slack per unit of coordinate magnitude
     uint32_t oct_inv;  // dx>=0 ? 4 : 0 | dy>=0 ? 2 : 0 | dz>=0 ? 1 : 0
 };
 
@@ -78,7 +79,6 @@ RPT_D WideRay make_wide_ray(f3 o, f3 d) {
     r.o = o;
     r.d = d;
     r.idir = mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-    r.pad_scale = mk3(fabsf(r.idir.x) * 4.8e-7f, fabsf(r.idir.y) * 4.8e-7f, fabsf(r.idir.z) * 4.8e-7f);
     r.oct_inv = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
     return r;
 }
@@ -144,46 +144,59 @@ RPT_D uint32_t test_four(uint32_t magic, uint32_t nx, uint32_t ny, uint32_t nz, 
 
 // ---- traversal as a resumable cursor -------------------------------------------------------
 // The per-ray state between steps.  A step is either one node visit (`visit_node`) or one
-// ray/triangle test (`test_triangle`); `advance` pops the next group of child nodes.  The device
-// kernels interleave these steps across the lanes of a warp (ray refill); the plain loop
-// `wide_intersect` below composes them for one ray.
-//   ngroup = (first child node, permuted hits << 24 | inner-slot mask): child nodes still to visit
+// ray/triangle test (`test_triangle`).  The device kernels interleave these steps across the lanes
+// of a warp (ray refill); the plain loop `wide_intersect` below composes them for one ray.
+//   next   = the node to visit next (kNoNode: traversal finished).  It is chosen at the END of a visit — before
+//            that node's triangles are tested — so that its cache lines can be prefetched while the triangle
+//            records are in flight; the choice depends on the box tests only, never on the triangle results.
+//   ngroup = (first child node, permuted hits << 24 | inner-slot mask): siblings of `next` still to visit
 //   tgroup = (first triangle of the node, 24-bit hit mask), tvalid = the node's valid-triangle bits:
 //            triangle bit k is the node's popc(tvalid below k)-th triangle
+constexpr uint32_t kNoNode = 0xFFFFFFFFu;
+// Measured on B200 (BreakTime proxy): prefetch.global.L1 of the next node makes extend 1.7x SLOWER — at 32 warps
+// per SM the prefetched lines (256 B per lane) overflow what is left of the L1 next to 150 KB of shared memory
+// and evict the top of the tree.  Kept as a switch for the record; off.
+constexpr bool kPrefetchNextNode = false;
+
 template <bool NEAREST>
 struct WideCursor {
     WideRay ray;
-    float best_t;   // current culling bound: best hit so far (nearest) or max_t (any)
-    float max_t;
-    WideHit res;
+    float best_t;      // culling bound: nearest accepted t so far (nearest; 1e6 = none) / min(max_t, 1e6) (any)
+    float hit_t;       // t of the accepted hit (== best_t for nearest)
+    uint32_t hit_tri;  // kNoNode: no hit; else wide triangle | back-face << 31
+    uint32_t next;
     uint2 ngroup, tgroup;
     uint32_t tvalid;
 
     RPT_D void begin(f3 ro, f3 rd, float max_t_) {
-        res = WideHit{1000000.0f, 0u, false, false};
-        max_t = max_t_;
         ray = make_wide_ray(ro, rd);
-        best_t = NEAREST ? res.t : fminf(max_t_, res.t);
-        ngroup = make_uint2(0u, 0x80000000u);  // the root, as "child bit 31 of a virtual parent"
+        best_t = NEAREST ? 1000000.0f : fminf(max_t_, 1000000.0f);  // TraceResult::default().t, intersection.rs:68
+        hit_t = 1000000.0f;
+        hit_tri = kNoNode;
+        next = 0u;  // the root
+        ngroup = make_uint2(0u, 0u);
         tgroup = make_uint2(0u, 0u);
         tvalid = 0u;
         // a ray with a non-finite component hits nothing in the reference either (every slab test
         // compares false); without this the NaN-ignoring min/max would visit every node
-        if (!(finite3(ro) && finite3(rd))) ngroup.y = 0u;
+        if (!(finite3(ro) && finite3(rd))) next = kNoNode;
     }
-    RPT_D bool has_nodes() const { return ngroup.y > 0x00FFFFFFu; }
+    RPT_D bool has_nodes() const { return next != kNoNode; }
+    RPT_D WideHit result() const { return WideHit{hit_t, hit_tri & 0x7FFFFFFFu, hit_tri != kNoNode, hit_tri != kNoNode && (hit_tri >> 31) != 0u}; }
     RPT_D bool has_triangles() const { return tgroup.y != 0u; }
+    // Drop everything still to be traversed (an any-hit query that is already decided).
+    template <class Stack>
+    RPT_D void abandon(Stack& stack) {
+        next = kNoNode;
+        ngroup.y = 0u;
+        tgroup.y = 0u;
+        stack.clear();
+    }
 
-    // Pops the nearest pending child of ngroup and tests its eight children.
+    // Tests the eight children of `next`, then picks (and prefetches) the node to visit after it.
     template <class Stack>
     RPT_D void visit_node(const WideScene& s, Stack& stack) {
-        const uint32_t hits = ngroup.y;
-        const int bit = highest_bit(hits);
-        ngroup.y &= ~(1u << bit);
-        if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
-        const uint32_t slot = ((uint32_t)bit - 24u) ^ ray.oct_inv;
-        const uint32_t rel = (uint32_t)popcount(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
-        const uint4* node = s.nodes + 5u * (size_t)(ngroup.x + rel);
+        const uint4* node = s.nodes + 5u * (size_t)next;
         const uint4 n0 = __ldg(node), n1 = __ldg(node + 1), n2 = __ldg(node + 2), n3 = __ldg(node + 3), n4 = __ldg(node + 4);
 
         const f3 p = mk3(as_float(n0.x), as_float(n0.y), as_float(n0.z));
@@ -191,12 +204,12 @@ struct WideCursor {
         const f3 adj = cell * ray.idir;
         // Push the planes out so rounding can never cull a box the exact arithmetic would enter.  p - o, its
         // product with idir and the final FMA are each correctly rounded, i.e. off by < 2^-23 of |p - o| resp.
-        // of the box extent (<= 256 cells): pad by 2^-21 of both.  Folding the -1024 bias of the fp16
+        // of the box extent (<= 256 cells): pad by 2^-21 (4.8e-7) of both.  Folding the -1024 bias of the fp16
         // de-quantisation into the addend rounds it at magnitude 1024 |adj|, i.e. by < 2^-14 |adj|: 512 more
         // cells in the same pad term cover that four times over.
         const f3 rel_o = p - ray.o;
-        const f3 apad = mk3(fmaf(768.0f, cell.x, fabsf(rel_o.x)) * ray.pad_scale.x, fmaf(768.0f, cell.y, fabsf(rel_o.y)) * ray.pad_scale.y,
-                            fmaf(768.0f, cell.z, fabsf(rel_o.z)) * ray.pad_scale.z);
+        const f3 apad = mk3(fabsf(fmaf(768.0f, cell.x, fabsf(rel_o.x)) * ray.idir.x) * 4.8e-7f, fabsf(fmaf(768.0f, cell.y, fabsf(rel_o.y)) * ray.idir.y) * 4.8e-7f,
+                            fabsf(fmaf(768.0f, cell.z, fabsf(rel_o.z)) * ray.idir.z) * 4.8e-7f);
         const f3 org = rel_o * ray.idir;
         const f3 org_near = mk3(fmaf(adj.x, -1024.0f, org.x - apad.x), fmaf(adj.y, -1024.0f, org.y - apad.y), fmaf(adj.z, -1024.0f, org.z - apad.z));
         const f3 org_far = mk3(fmaf(adj.x, -1024.0f, org.x + apad.x), fmaf(adj.y, -1024.0f, org.y + apad.y), fmaf(adj.z, -1024.0f, org.z + apad.z));
@@ -208,11 +221,31 @@ struct WideCursor {
         h |= test_four<4u>(s.half_1024_bytes, nx ? n3.w : n2.y, ny ? n4.y : n2.w, nz ? n4.w : n3.y, nx ? n2.y : n3.w, ny ? n2.w : n4.y, nz ? n3.y : n4.w, adj,
                            org_near, org_far, best_t);
         const uint32_t imask = n1.z >> 24;
-        ngroup.x = n1.x;
-        ngroup.y = (stack.permute(ray.oct_inv, (h >> 24) & imask) << 24) | imask;
         tgroup.x = n1.y;
         tvalid = n1.z & 0x00FFFFFFu;
         tgroup.y = h & tvalid;
+
+        // ---- the node after this one: its nearest hit child, else the nearest pending sibling, else the stack
+        const uint32_t child_hits = stack.permute(ray.oct_inv, (h >> 24) & imask) << 24;
+        if (child_hits != 0u) {
+            if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
+            ngroup = make_uint2(n1.x, child_hits | imask);
+        } else if (ngroup.y <= 0x00FFFFFFu && !stack.empty()) {
+            ngroup = stack.pop();
+        }
+        if (ngroup.y > 0x00FFFFFFu) {
+            const int bit = highest_bit(ngroup.y);
+            const uint32_t slot = ((uint32_t)bit - 24u) ^ ray.oct_inv;
+            next = ngroup.x + (uint32_t)popcount(ngroup.y & ~(0xFFFFFFFFu << slot) & 0xFFu);
+            ngroup.y &= ~(1u << bit);
+            if (kPrefetchNextNode) {
+                const char* line = reinterpret_cast<const char*>(s.nodes + 5u * (size_t)next);
+                prefetch_l1(line);
+                prefetch_l1(line + 64);  // an 80-byte node straddles two 128-byte lines half of the time
+            }
+        } else {
+            next = kNoNode;
+        }
     }
     // Tests the next pending triangle; returns true when an any-hit query is decided.
     RPT_D bool test_triangle(const WideScene& s) {
@@ -223,31 +256,21 @@ struct WideCursor {
         const float4 a = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
         float t;
         bool back;
-        if (ray_triangle(ray.o, ray.d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t, back) && t > 0.001f && t < res.t &&
-            (NEAREST || t <= max_t)) {
-            res.t = t;
-            res.triangle = ti;
-            res.hit = true;
-            res.backface = back;
+        // accept 0.001 < t < best so far (nearest) resp. t <= max_t and t < 1e6 (any), intersection.rs:195
+        if (ray_triangle(ray.o, ray.d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t, back) && t > 0.001f &&
+            (NEAREST ? t < best_t : (t <= best_t && t < 1000000.0f))) {
+            hit_t = t;
+            hit_tri = ti | (back ? 0x80000000u : 0u);
             if (!NEAREST) return true;
             best_t = t;
         }
         return false;
     }
-    // After the triangles: make sure ngroup holds child nodes, popping the stack; false when the ray is done.
-    template <class Stack>
-    RPT_D bool advance(Stack& stack) {
-        if (ngroup.y <= 0x00FFFFFFu) {
-            if (stack.empty()) return false;
-            ngroup = stack.pop();
-        }
-        return true;
-    }
 };
 
 // Nearest hit (NEAREST = true, `t < best`) or any hit with t <= max_t (NEAREST = false), with the
 // reference's acceptance window t > 0.001 (intersection.rs:195).  Stack: push(uint2), pop(),
-// empty(), permute(octant, child set).
+// empty(), clear(), permute(octant, child set).
 template <bool NEAREST, class Stack>
 RPT_D WideHit wide_intersect(const WideScene& s, f3 ro, f3 rd, float max_t, Stack& stack) {
     WideCursor<NEAREST> c;
@@ -255,10 +278,9 @@ RPT_D WideHit wide_intersect(const WideScene& s, f3 ro, f3 rd, float max_t, Stac
     while (c.has_nodes()) {
         c.visit_node(s, stack);
         while (c.has_triangles())
-            if (c.test_triangle(s)) return c.res;
-        if (!c.advance(stack)) break;
+            if (c.test_triangle(s)) return c.result();
     }
-    return c.res;
+    return c.result();
 }
 
 }  // namespace rpt

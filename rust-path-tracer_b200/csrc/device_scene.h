@@ -113,9 +113,6 @@ struct WaveLaunch {
     cudaStream_t stream;
     int trace_blocks_per_sm;  // resident 128-thread blocks per SM of the trace kernels
     int refill_below;         // refill idle lanes once fewer than this many lanes of a warp hold a ray
-    bool pooled_triangles;    // wf_trace_coop_kernel (per-warp triangle pool) instead of wf_trace_kernel
-    uint32_t flush_at;        // test the pool once it holds this many pairs (<= 32) ...
-    int flush_waiting;        // ... or once this many lanes have nothing left to do but wait for it
 };
 
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole);

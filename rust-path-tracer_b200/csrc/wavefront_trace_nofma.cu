@@ -30,6 +30,7 @@ struct SmemStack {
     }
     __device__ __forceinline__ uint2 pop() { --n; return column[n * 32]; }
     __device__ __forceinline__ bool empty() const { return n == 0; }
+    __device__ __forceinline__ void clear() { n = 0; }
 };
 
 // Append `value` to a queue for every lane with `pred`; one atomic per warp.
@@ -137,13 +138,12 @@ __global__ void __launch_bounds__(kTraceBlock, 8) wf_trace_kernel(WideScene bvh,
             if (c.has_nodes()) c.visit_node(bvh, st);  // (only a non-finite ray starts without nodes)
             while (c.has_triangles())
                 if (c.test_triangle(bvh)) { finished = true; break; }
-            if (!finished && !c.advance(st)) finished = true;
+            if (!c.has_nodes()) finished = true;
             if (finished) {
                 busy = false;
                 if (NEAREST) {  // every traced slot gets a record; kMissRecord marks "no hit" for wf_compact_kernel
-                    s.hit[item] = c.res.hit ? make_uint2(__float_as_uint(c.res.t), c.res.triangle | (c.res.backface ? 0x80000000u : 0u))
-                                            : make_uint2(0u, kMissRecord);
-                } else if (!c.res.hit) {  // unoccluded: radiance += mask_nan(contribution) (lib.rs:164; masked when queued)
+                    s.hit[item] = make_uint2(__float_as_uint(c.best_t), c.hit_tri);  // kMissRecord == kNoNode marks "no hit"
+                } else if (c.hit_tri == kNoNode) {  // unoccluded: radiance += mask_nan(contribution) (lib.rs:164; masked when queued)
                     const uint32_t slot = __float_as_uint(s.sh_d[item].w);
                     const float4 add = s.sh_c[item];
                     float4 r = s.rad[slot];
@@ -153,181 +153,6 @@ __global__ void __launch_bounds__(kTraceBlock, 8) wf_trace_kernel(WideScene bvh,
                 break;
             }
             if (!exhausted && __popc(__activemask()) < refill_below) break;
-        }
-    }
-}
-
-// ---- cooperative variant: ray/triangle tests are pooled per warp -------------------------------
-// In the kernel above a lane that reaches triangles tests them itself while the other lanes of the warp wait:
-// on incoherent bounces that loop runs with ~3 of 32 lanes enabled and costs as many issue slots as all the
-// node visits (ncu, profiles/).  Here every round is warp-converged: lanes with pending child nodes visit one
-// node; the triangles they hit are appended as (owner lane, triangle) pairs to a per-warp ring in shared
-// memory (two ballots give every lane its offset); whenever the ring holds a full warp's worth — or lanes are
-// only waiting for it — all 32 lanes take one pair each, read the owner's ray from a shared slab, run the exact
-// ray/triangle test and merge the result with a 64-bit atomicMin on (t bits, triangle, back-face) in the
-// owner's result slot.  A lane's culling bound is refreshed from its slot after every test pass, so deferring a
-// test only ever makes traversal visit more nodes, never fewer; equal-t ties go to the lower wide triangle
-// index whatever the scheduling (deterministic).  A ray is finished when its stack is empty and none of its
-// pairs is queued.
-constexpr uint32_t kPoolCapacity = 128;   // < 32 pairs carried over + at most 3 per lane and round
-constexpr uint32_t kPoolOwnerShift = 27;  // pair = owner lane << 27 | wide triangle index (rpt_upload_world checks the range)
-
-template <bool NEAREST>
-__global__ void __launch_bounds__(kTraceBlock, 8) wf_trace_coop_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
-                                                                       int refill_below, uint32_t flush_at, int flush_waiting) {
-    __shared__ uint2 slabs[kTraceWarps][kWideStackCapacity][32];
-    __shared__ float4 ray_slab[kTraceWarps][2][32];  // [0]: origin.xyz  [1]: direction.xyz, max_t
-    __shared__ unsigned long long best_slab[kTraceWarps][32];
-    __shared__ uint32_t pool_slab[kTraceWarps][kPoolCapacity];
-    __shared__ uint8_t perm_table[8 * 256];
-    for (uint32_t i = threadIdx.x; i < 8u * 256u; i += kTraceBlock) perm_table[i] = (uint8_t)octant_permute(i >> 8, i & 0xFFu);
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t lanes_below = (1u << lane) - 1u;
-    const uint32_t n = NEAREST ? (identity ? n_identity : (in_queue ? s.ctl->n_ext[1] : s.ctl->n_ext[0])) : s.ctl->n_shadow;
-    const uint32_t* __restrict__ queue = in_queue ? s.q_ext[1] : s.q_ext[0];
-    uint32_t* fetch = NEAREST ? &s.ctl->fetch_extend : &s.ctl->fetch_shadow;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.counters + (NEAREST ? 1 : 2), (unsigned long long)n);
-
-    float4* const ray_o = ray_slab[warp][0];
-    float4* const ray_d = ray_slab[warp][1];
-    unsigned long long* const best = best_slab[warp];
-    uint32_t* const pool = pool_slab[warp];
-    // "no hit yet": nearest accepts t < 1e6 (intersection.rs:68,195), i.e. keys below bits(1e6) << 32
-    const unsigned long long kNoHit = NEAREST ? ((unsigned long long)__float_as_uint(1000000.0f) << 32) : ~0ull;
-
-    SmemStack st{&slabs[warp][0][lane], 0, perm_table};
-    WideCursor<NEAREST> c;
-    c.ngroup = make_uint2(0u, 0u);
-    uint32_t item = 0;       // path slot (NEAREST) / shadow-queue index (ANY)
-    uint32_t tris = 0;       // triangle hits of this lane's last node visit not yet in the pool
-    bool busy = false;       // this lane holds an unfinished ray
-    bool exhausted = false;  // the cursor ran past the end of the queue (warp-uniform)
-    bool tested = false;     // a test pass ran since the lanes last read their result slots (warp-uniform)
-    uint32_t count = 0;      // pairs in the ring (warp-uniform)
-    uint32_t head_seq = 0;   // pairs tested so far; pair number q sits in pool[q % kPoolCapacity] (warp-uniform)
-    uint32_t last_seq = 0;   // number after this lane's newest pair: all of its pairs are tested once head_seq reaches it
-
-    // All 32 lanes: test the first min(count, 32) pairs of the ring.
-    auto test_pool = [&]() {
-        const uint32_t take = min(count, 32u);
-        if (lane < take) {
-            const uint32_t pair = pool[(head_seq + lane) % kPoolCapacity];
-            const uint32_t owner = pair >> kPoolOwnerShift, ti = pair & ((1u << kPoolOwnerShift) - 1u);
-            const float4* rec = bvh.tri_pos + 3u * (size_t)ti;
-            const float4 a = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
-            const float4 o = ray_o[owner], d = ray_d[owner];
-            float t;
-            bool back;
-            if (ray_triangle(xyz(o), xyz(d), xyz(a), xyz(e1), xyz(e2), t, back) && t > 0.001f && (NEAREST || (t <= d.w && t < 1000000.0f))) {
-                const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (ti << 1) | (back ? 1u : 0u);
-                if (key < best[owner]) atomicMin(best + owner, key);
-            }
-        }
-        count -= take;
-        head_seq += take;
-        tested = true;
-        __syncwarp();
-    };
-
-    for (;;) {
-        // ---- refill idle lanes ---------------------------------------------------------------------
-        if (!exhausted) {
-            const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !busy);
-            if (idle) {
-                const int leader = __ffs((int)idle) - 1;
-                uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                const uint32_t i = base + (uint32_t)__popc(idle & lanes_below);
-                exhausted = base + (uint32_t)__popc(idle) >= n;
-                if (!busy && i < n) {
-                    float4 o, dv;
-                    float max_t = 0.0f;
-                    if (NEAREST) {
-                        item = identity ? i : __ldg(queue + i);
-                        o = s.ray_o[item];
-                        dv = s.ray_d[item];
-                    } else {
-                        item = __ldg(s.q_shadow + i);
-                        o = s.sh_o[item];
-                        dv = s.sh_d[item];
-                        max_t = o.w;
-                    }
-                    c.begin(xyz(o), xyz(dv), max_t);
-                    st.n = 0;
-                    busy = true;
-                    ray_o[lane] = o;
-                    ray_d[lane] = make_float4(dv.x, dv.y, dv.z, max_t);
-                    best[lane] = kNoHit;
-                    last_seq = head_seq;
-                }
-                __syncwarp();
-            }
-        }
-        uint32_t live = __ballot_sync(0xFFFFFFFFu, busy);
-        if (live == 0u) {
-            if (exhausted) break;
-            continue;
-        }
-
-        // ---- warp-converged rounds -----------------------------------------------------------------
-        for (;;) {
-            if (tested) {  // results moved: tighten the culling bound / stop an occluded shadow ray
-                tested = false;
-                if (busy) {
-                    const unsigned long long key = best[lane];
-                    if (NEAREST) c.best_t = fminf(c.best_t, __uint_as_float((uint32_t)(key >> 32)));
-                    else if (key != kNoHit) { c.ngroup.y = 0u; st.n = 0; tris = 0u; }  // queued pairs still have to drain
-                }
-            }
-            if (busy && tris == 0u && c.has_nodes()) {
-                c.visit_node(bvh, st);
-                tris = c.tgroup.y;
-                c.advance(st);
-            }
-            // append up to three of this lane's triangle hits to the ring; two ballots place every lane
-            {
-                const uint32_t mine = min((uint32_t)__popc(tris), 3u);
-                const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, (mine & 1u) != 0u), b1 = __ballot_sync(0xFFFFFFFFu, (mine & 2u) != 0u);
-                if ((b0 | b1) != 0u) {
-                    if (mine != 0u) {
-                        uint32_t q = head_seq + count + (uint32_t)__popc(b0 & lanes_below) + 2u * (uint32_t)__popc(b1 & lanes_below);
-                        const uint32_t tag = lane << kPoolOwnerShift;
-                        last_seq = q + mine;
-                        for (uint32_t j = 0; j < mine; ++j, ++q) {
-                            const int k = highest_bit(tris);
-                            tris &= ~(1u << k);
-                            pool[q % kPoolCapacity] = tag | (c.tgroup.x + (uint32_t)__popc(c.tvalid & ~(0xFFFFFFFFu << k)));
-                        }
-                    }
-                    count += (uint32_t)__popc(b0) + 2u * (uint32_t)__popc(b1);
-                    __syncwarp();
-                    while (count >= 32u) test_pool();
-                }
-            }
-            const uint32_t through = __ballot_sync(0xFFFFFFFFu, busy && tris == 0u && !c.has_nodes());  // nothing left to traverse
-            uint32_t waiting = __ballot_sync(0xFFFFFFFFu, busy && tris == 0u && !c.has_nodes() && (int)(head_seq - last_seq) < 0);
-            if (count != 0u && (count >= flush_at || __popc(waiting) >= flush_waiting || through == live)) {
-                while (count != 0u) test_pool();
-                waiting = 0u;
-            }
-            const uint32_t done = through & ~waiting;
-            if ((done >> lane) & 1u) {
-                busy = false;
-                const unsigned long long key = best[lane];
-                if (NEAREST) {  // every traced slot gets a record; kMissRecord marks "no hit" for wf_compact_kernel
-                    s.hit[item] = key != kNoHit ? make_uint2((uint32_t)(key >> 32), ((uint32_t)key >> 1) | ((uint32_t)key << 31)) : make_uint2(0u, kMissRecord);
-                } else if (key == kNoHit) {  // unoccluded: radiance += mask_nan(contribution) (lib.rs:164; masked when queued)
-                    const uint32_t slot = __float_as_uint(s.sh_d[item].w);
-                    const float4 add = s.sh_c[item];
-                    float4 r = s.rad[slot];
-                    r.x += add.x; r.y += add.y; r.z += add.z;
-                    s.rad[slot] = r;
-                }
-            }
-            live &= ~done;
-            if (live == 0u || (!exhausted && __popc(live) < refill_below)) break;
         }
     }
 }
@@ -452,21 +277,14 @@ void launch_wf_generate(const WaveLaunch& l, const FrameParams& f, const WaveSta
     wf_generate_kernel<<<l.grid * 2, 256, 0, l.stream>>>(f, s, d, rng);
 }
 void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, int in_queue, bool identity_queue, uint32_t n_identity) {
-    if (l.pooled_triangles)
-        wf_trace_coop_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below,
-                                                                                                 l.flush_at, l.flush_waiting);
-    else
-        wf_trace_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below);
+    wf_trace_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below);
     wf_compact_kernel<<<l.grid * 2, kCompactBlock, 0, l.stream>>>(s, in_queue, identity_queue, n_identity);
 }
 void launch_wf_compact_shaded(const WaveLaunch& l, const WaveState& s, int out_queue) {
     wf_compact_shaded_kernel<<<l.grid * 2, kCompactBlock, 0, l.stream>>>(s, out_queue);
 }
 void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState& s) {
-    if (l.pooled_triangles)
-        wf_trace_coop_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.flush_at, l.flush_waiting);
-    else
-        wf_trace_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below);
+    wf_trace_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below);
 }
 void launch_wf_export_primary(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, const WaveDesc& d, uint32_t* ids) {
     wf_export_primary_kernel<<<(d.npix + 255) / 256, 256, 0, l.stream>>>(bvh, s, d, ids);

@@ -180,30 +180,37 @@ int trace_gpu(const std::string& scene_path, const char* skybox_path, std::share
         if ((rc = rpt_write_output(ctx, init.data(), pixel_count)) != RPT_OK) return fail("rpt_write_output");
     }
 
-    std::vector<float> image_buffer(pixel_count * 3);
+    // the per-batch readback lands in page-locked staging memory (the reference reads through a mapped staging buffer too)
+    float* image_buffer = nullptr;
+    if ((rc = rpt_host_alloc(pixel_count * 3 * sizeof(float), reinterpret_cast<void**>(&image_buffer))) != RPT_OK) return fail("rpt_host_alloc");
+    auto fail_loop = [&](const char* what) {
+        rpt_host_free(image_buffer);
+        return fail(what);
+    };
     while (state->running.load(std::memory_order_relaxed)) {
         const uint32_t sync_rate = state->sync_rate.load(std::memory_order_relaxed);
         const bool flush = state->interacting.load(std::memory_order_relaxed) || state->dirty.load(std::memory_order_relaxed);
         const uint32_t batch = flush ? 1u : sync_rate;  // the reference breaks out of its dispatch loop after one sample when flushing
-        if ((rc = rpt_enqueue(ctx, batch)) != RPT_OK) return fail("rpt_enqueue");
-        if ((rc = rpt_sync(ctx)) != RPT_OK) return fail("rpt_sync");
+        if ((rc = rpt_enqueue(ctx, batch)) != RPT_OK) return fail_loop("rpt_enqueue");
+        if ((rc = rpt_sync(ctx)) != RPT_OK) return fail_loop("rpt_sync");
         state->samples.fetch_add(batch, std::memory_order_relaxed);
 
         const float sample_count = (float)state->samples.load(std::memory_order_relaxed);
-        if ((rc = rpt_read_framebuffer(ctx, image_buffer.data(), pixel_count, sample_count)) != RPT_OK) return fail("rpt_read_framebuffer");
+        if ((rc = rpt_read_framebuffer(ctx, image_buffer, pixel_count, sample_count)) != RPT_OK) return fail_loop("rpt_read_framebuffer");
         {
             std::unique_lock<std::shared_mutex> l(state->framebuffer_lock);
-            state->framebuffer = image_buffer;
+            state->framebuffer.assign(image_buffer, image_buffer + pixel_count * 3);
         }
         if (flush) {  // src/trace.rs:216-222
             state->dirty.store(false, std::memory_order_relaxed);
             state->samples.store(0, std::memory_order_relaxed);
             const RptTracingConfig cfg = state->read_config();
-            if ((rc = rpt_set_config(ctx, &cfg)) != RPT_OK) return fail("rpt_set_config");
-            if ((rc = rpt_write_output(ctx, nullptr, pixel_count)) != RPT_OK) return fail("rpt_write_output");
-            if ((rc = rpt_write_rng(ctx, seeds(), pixel_count)) != RPT_OK) return fail("rpt_write_rng");
+            if ((rc = rpt_set_config(ctx, &cfg)) != RPT_OK) return fail_loop("rpt_set_config");
+            if ((rc = rpt_write_output(ctx, nullptr, pixel_count)) != RPT_OK) return fail_loop("rpt_write_output");
+            if ((rc = rpt_write_rng(ctx, seeds(), pixel_count)) != RPT_OK) return fail_loop("rpt_write_rng");
         }
     }
+    rpt_host_free(image_buffer);
     rpt_destroy(ctx);
     return RPT_OK;
 }

@@ -235,6 +235,13 @@ def trace_gpu(scene_path: str, skybox_path: str | None, state: TracingState, dev
     seeds = make_rng_seeds(width, height, use_blue_noise=state.use_blue_noise)
 
     with Renderer(device, pipeline) as r:
+        # the buffers that cross the boundary every batch live in page-locked memory (rpt_host_alloc)
+        pinned_seeds = capi.pinned_empty(seeds.shape, np.uint32)
+        pinned_seeds[...] = seeds
+        seeds = pinned_seeds
+        framebuffer = capi.pinned_empty(state.framebuffer.shape, np.float32)
+        framebuffer[...] = state.framebuffer
+        state.framebuffer = framebuffer
         r.upload_world(world, skybox)
         r.set_config(state.config)
         r.write_rng(seeds)

@@ -20,6 +20,7 @@ struct LocalStack {
     void push(rpt::uint2 v) { data[n++] = v; if (n > high_water) high_water = n; }
     rpt::uint2 pop() { return data[--n]; }
     bool empty() const { return n == 0; }
+    void clear() { n = 0; }
     uint32_t permute(uint32_t oct, uint32_t m) const { return rpt::octant_permute(oct, m); }
 };
 }  // namespace
