@@ -134,7 +134,7 @@ struct rpt_context {
 
     // wave state
     uint32_t wave_capacity = 0;
-    DevBuf<float4> w_ray_o, w_ray_d, w_thr, w_rad, w_mis_a, w_mis_b, w_sh_o, w_sh_d, w_sh_c;
+    DevBuf<float4> w_ray_o, w_ray_d, w_thr, w_rad, w_sh_o, w_sh_d, w_sh_c;
     DevBuf<uint2> w_hit;
     DevBuf<uint32_t> w_q0, w_q1, w_qhit, w_qmiss, w_qshaded, w_qshadow;
     DevBuf<WaveCtl> w_ctl;
@@ -257,7 +257,7 @@ WideWorld wide_world(const rpt_context* c) {
 WaveState wave_state(rpt_context* c) {
     WaveState s{};
     s.ray_o = c->w_ray_o.p; s.ray_d = c->w_ray_d.p; s.thr = c->w_thr.p; s.rad = c->w_rad.p;
-    s.mis_a = c->w_mis_a.p; s.mis_b = c->w_mis_b.p; s.hit = c->w_hit.p;
+    s.hit = c->w_hit.p;
     s.sh_o = c->w_sh_o.p; s.sh_d = c->w_sh_d.p; s.sh_c = c->w_sh_c.p;
     s.q_ext[0] = c->w_q0.p; s.q_ext[1] = c->w_q1.p; s.q_hit = c->w_qhit.p; s.q_miss = c->w_qmiss.p;
     s.q_shaded = c->w_qshaded.p; s.q_shadow = c->w_qshadow.p;
@@ -269,7 +269,7 @@ WaveState wave_state(rpt_context* c) {
 int ensure_wave(rpt_context* c, uint32_t slots) {
     if (slots <= c->wave_capacity) return RPT_OK;
     RPT_CUDA(c, c->w_ray_o.alloc(slots)); RPT_CUDA(c, c->w_ray_d.alloc(slots)); RPT_CUDA(c, c->w_thr.alloc(slots));
-    RPT_CUDA(c, c->w_rad.alloc(slots)); RPT_CUDA(c, c->w_mis_a.alloc(slots)); RPT_CUDA(c, c->w_mis_b.alloc(slots));
+    RPT_CUDA(c, c->w_rad.alloc(slots));
     RPT_CUDA(c, c->w_sh_o.alloc(slots)); RPT_CUDA(c, c->w_sh_d.alloc(slots)); RPT_CUDA(c, c->w_sh_c.alloc(slots));
     RPT_CUDA(c, c->w_hit.alloc(slots));
     RPT_CUDA(c, c->w_q0.alloc(slots)); RPT_CUDA(c, c->w_q1.alloc(slots)); RPT_CUDA(c, c->w_qhit.alloc(slots)); RPT_CUDA(c, c->w_qmiss.alloc(slots));
@@ -408,7 +408,7 @@ extern "C" int rpt_destroy(rpt_context* c) {
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     for (auto& ev : c->timed) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     c->drain_stage_events();
-    for (auto* b : {&c->w_ray_o, &c->w_ray_d, &c->w_thr, &c->w_rad, &c->w_mis_a, &c->w_mis_b, &c->w_sh_o, &c->w_sh_d, &c->w_sh_c, &c->d_tri_pos,
+    for (auto* b : {&c->w_ray_o, &c->w_ray_d, &c->w_thr, &c->w_rad, &c->w_sh_o, &c->w_sh_d, &c->w_sh_c, &c->d_tri_pos,
                     &c->d_tri_shade, &c->d_tri_tangent, &c->d_sky, &c->d_output})
         b->release();
     c->w_hit.release(); c->w_q0.release(); c->w_q1.release(); c->w_qhit.release(); c->w_qmiss.release(); c->w_qshaded.release();
@@ -523,6 +523,7 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
             bins.push_back(bin);
         }
         if (status != RPT_OK) return c->fail(status, "light-pick table references a triangle out of range");
+        if (records.size() >= (1u << 23)) return c->fail(RPT_ERR_UNSUPPORTED, "more than 2^23 emissive triangles (the path state keeps the sampled light in 23 bits)");
     }
 
     // ---- uploads

@@ -81,12 +81,10 @@ struct WaveCtl {
 
 // Path state of one wave, structure-of-arrays over `slots` path slots.
 struct WaveState {
-    float4* ray_o;   // origin.xyz, -
-    float4* ray_d;   // direction.xyz, bits(rng dimension | last lobe << 8)
+    float4* ray_o;   // origin.xyz, Russian-roulette probability the throughput was last divided by (1 if none)
+    float4* ray_d;   // direction.xyz, bits(rng dimension | last lobe << 8 | light record of the last NEE sample << 9)
     float4* thr;     // throughput.xyz, pdf of the last BSDF sample
     float4* rad;     // radiance of this pixel-sample so far
-    float4* mis_a;   // last BSDF spectrum.xyz, bits(light record sampled by NEE)
-    float4* mis_b;   // throughput before the last bounce .xyz, bits(wide triangle of that light)
     uint2* hit;      // bits(t), wide triangle | backface << 31
     float4* sh_o;    // shadow rays, indexed like q_hit: origin.xyz, max_t
     float4* sh_d;    //               direction.xyz, bits(slot)

@@ -37,17 +37,28 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
     const uint32_t n = s.ctl->n_hit;
     const bool nee = f.nee != RPT_NEE_NONE;
     const bool last_bounce = bounce + 1u >= f.max_bounces;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // The first two levels of the dependent load chain (q_hit[i] -> slot -> hit[slot]) are software-pipelined two
+    // iterations ahead, so an iteration starts with its slot and hit record already in registers and goes
+    // straight to the path-state and triangle fetches.
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t slot_next = i < n ? __ldg(s.q_hit + i) : 0u;
+    uint32_t slot_after = i + stride < n ? __ldg(s.q_hit + i + stride) : 0u;
+    uint2 hit_next = i < n ? s.hit[slot_next] : make_uint2(0u, 0u);
+    for (; i < n; i += stride) {
         bool want_shadow = false, want_next = false;
-        const uint32_t slot = __ldg(s.q_hit + i);
-        const uint2 hr = s.hit[slot];
+        const uint32_t slot = slot_next;
+        const uint2 hr = hit_next;
+        slot_next = slot_after;
+        if (i + stride < n) hit_next = s.hit[slot_next];
+        if (i + 2u * stride < n) slot_after = __ldg(s.q_hit + i + 2u * stride);
         const float t = __uint_as_float(hr.x);
         const uint32_t tri = hr.y & 0x7FFFFFFFu;
         const bool backface = (hr.y >> 31) != 0u;
         const float4 o4 = s.ray_o[slot], d4 = s.ray_d[slot], thr4 = s.thr[slot];
         const f3 ro = xyz(o4), rd = xyz(d4);
         const f3 throughput = xyz(thr4);
-        const uint32_t flags = __float_as_uint(d4.w);
+        const uint32_t flags = __float_as_uint(d4.w);  // rng dimension | last lobe << 8 | light record of the last NEE sample << 9
         const uint32_t last_lobe = (flags >> 8) & 1u;
         const uint2 seed = __ldg(rng + wave_pixel(d, slot % d.npix));
         Rng rstate{seed.x + slot / d.npix + seed.y, flags & 0xFFu};
@@ -69,15 +80,17 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
                 s.rad[slot] = r;
                 alive = false;
             } else if (f.nee == RPT_NEE_MIS) {  // calculate_bsdf_mis_contribution, light_pick.rs:179-199
-                const float4 ma = s.mis_a[slot], mb = s.mis_b[slot];
+                // The reference multiplies the throughput BEFORE the last bounce by that bounce's spectrum / pdf; that
+                // product is the current throughput times the Russian-roulette probability it was divided by
+                // (o4.w; 1 when no roulette ran), so no per-path copy of either factor is kept.
+                const LightRecord& L = w.lights[flags >> 9];
                 f3 c = splat3(0.0f);
-                if (tri == __float_as_uint(mb.w)) {
-                    const LightRecord& L = w.lights[__float_as_uint(ma.w)];
-                    const float lp = light_pdf(L.a_area.w, t, xyz(L.normal), rd);
+                if (tri == __float_as_uint(__ldg(&L.e2_tri).w)) {
+                    const float4 la = __ldg(&L.a_area);
+                    const float lp = light_pdf(la.w, t, xyz(__ldg(&L.normal)), rd);
                     if (lp > 0.0f) {
-                        const float bsdf_pdf = thr4.w;
-                        const float wgt = power_heuristic(bsdf_pdf, lp);
-                        c = xyz(mb) * ((xyz(ma) * xyz(L.emission) * wgt / bsdf_pdf) / L.e1_pdf.w);
+                        const float wgt = power_heuristic(thr4.w, lp);
+                        c = (throughput * o4.w) * ((xyz(__ldg(&L.emission)) * wgt) / __ldg(&L.e1_pdf).w);
                     }
                 }
                 c = mask_nan(c);
@@ -110,7 +123,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
             const float r1 = rstate.next(), r2 = rstate.next(), r3 = rstate.next();
             const BsdfSample bs = pbr_sample(bsdf, view, normal, mk3(r1, r2, r3));
 
-            uint32_t light_rec = 0, light_tri = 0;
+            uint32_t light_rec = 0;
             if (nee && bs.lobe == kLobeDiffuse && w.nbins > 0u) {  // sample_direct_lighting, light_pick.rs:100-173
                 const float l1 = rstate.next(), l2 = rstate.next();
                 uint32_t bin_i = (uint32_t)fminf(l1 * (float)w.nbins, 4294967040.0f);
@@ -120,7 +133,6 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
                 light_rec = l2 < bin.ratio ? bin.light_a : bin.light_b;
                 const LightRecord& L = w.lights[light_rec];
                 const float4 la = __ldg(&L.a_area), le1 = __ldg(&L.e1_pdf), le2 = __ldg(&L.e2_tri);
-                light_tri = __float_as_uint(le2.w);
                 const float q1 = rstate.next(), q2 = rstate.next();
                 const float sq = sqrtf(q1);
                 // (1-sq) a + sq(1-q2) b + sq q2 c  ==  a + sq(1-q2) e1 + sq q2 e2
@@ -150,20 +162,17 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
 
             if (!last_bounce) {
                 f3 next_thr = throughput * (bs.spectrum / bs.pdf);
+                float roulette = 1.0f;
                 want_next = true;
                 if (bounce > f.min_bounces) {  // Russian roulette, lib.rs:175-181
-                    const float prob = max_element(next_thr);
-                    if (rstate.next() > prob) want_next = false;
-                    next_thr = next_thr * (1.0f / prob);
+                    roulette = max_element(next_thr);
+                    if (rstate.next() > roulette) want_next = false;
+                    next_thr = next_thr * (1.0f / roulette);
                 }
                 if (want_next) {
-                    s.ray_o[slot] = mk4(hit + bs.direction * kEps, 0.0f);
-                    s.ray_d[slot] = mk4(bs.direction, __uint_as_float((rstate.dim & 0xFFu) | (bs.lobe << 8)));
+                    s.ray_o[slot] = mk4(hit + bs.direction * kEps, roulette);
+                    s.ray_d[slot] = mk4(bs.direction, __uint_as_float((rstate.dim & 0xFFu) | (bs.lobe << 8) | (light_rec << 9)));
                     s.thr[slot] = mk4(next_thr, bs.pdf);
-                    if (f.nee == RPT_NEE_MIS && bs.lobe == kLobeDiffuse) {
-                        s.mis_a[slot] = mk4(bs.spectrum, __uint_as_float(light_rec));
-                        s.mis_b[slot] = mk4(throughput, __uint_as_float(light_tri));
-                    }
                 }
             }
         }
