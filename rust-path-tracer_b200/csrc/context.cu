@@ -97,6 +97,7 @@ struct rpt_context {
     int pipeline = RPT_PIPELINE_WAVEFRONT;
     uint32_t wave_slots = kDefaultWaveSlots;
     // trace-kernel tunables (defaults chosen on B200; RPT_* env vars override for sweeps)
+    bool log_queues = false;  // RPT_LOG_QUEUES=1: print every bounce's queue lengths (syncs; for reading ncu captures)
     int trace_blocks_per_sm = 8;
     int refill_below = 20;
 
@@ -335,6 +336,13 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
         c->launch(RPT_STAGE_SHADE, [&] { launch_wf_shade(l, f, w, s, d, c->d_rng.p, b); launch_wf_compact_shaded(l, s, nxt); });
         c->kernel_launches++;  // shade = shading + queue compaction
         if (f.nee != RPT_NEE_NONE && c->nbins > 0) c->launch(RPT_STAGE_SHADOW, [&] { launch_wf_shadow(l, w.bvh, s); });
+        if (c->log_queues) {
+            WaveCtl ctl{};
+            cudaMemcpyAsync(&ctl, c->w_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, c->stream);
+            cudaStreamSynchronize(c->stream);
+            std::fprintf(stderr, "[rpt] bounce %u: extend traced %u rays -> %u hits, %u misses; %u shadow rays; %u paths go on\n", b,
+                         b == 0 ? nslots : ctl.n_ext[cur], ctl.n_hit, ctl.n_miss, ctl.n_shadow, ctl.n_ext[nxt]);
+        }
     }
     if (!primary_only) c->launch(RPT_STAGE_ACCUMULATE, [&] { launch_wf_accumulate(l, s, d, c->d_rng.p, c->d_output.p); });
     return c->cuda(cudaGetLastError(), "wavefront launch");
@@ -396,6 +404,7 @@ extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
     c->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("RPT_TRACE_BLOCKS_PER_SM")) c->trace_blocks_per_sm = std::max(1, atoi(v));
     if (const char* v = getenv("RPT_REFILL_BELOW")) c->refill_below = atoi(v);
+    if (const char* v = getenv("RPT_LOG_QUEUES")) c->log_queues = atoi(v) != 0;
     if (const char* v = getenv("RPT_WAVE_SLOTS")) c->wave_slots = (uint32_t)std::max(1024, atoi(v));
     *out_ctx = c;
     return RPT_OK;

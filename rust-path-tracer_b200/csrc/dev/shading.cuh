@@ -34,15 +34,6 @@ RPT_D uint32_t wrap_coord(int c, uint32_t size, uint32_t mask) {
     if (c >= 0 && mask != 0u) return (uint32_t)c & mask;
     return wrap_coord_general(c, size);
 }
-RPT_HD uint32_t pow2_mask(uint32_t size) { return (size & (size - 1u)) == 0u ? size - 1u : 0u; }
-
-// x / 255 for an integer 0 <= x <= 255, correctly rounded (== the IEEE division the CPU path does, checked for all
-// 256 values in tests/test_abi.py) without the division's special-case machinery: one Newton step on x * (1/255).
-RPT_D float unorm8(uint32_t x) {
-    const float xf = (float)x, r = 1.0f / 255.0f;
-    const float q = xf * r;
-    return fmaf(fmaf(-q, 255.0f, xf), r, q);
-}
 
 struct TexelRGBA8 {
     const uchar4* texels;

@@ -48,6 +48,17 @@ RPT_HD f3 xyz(float4 v) { return f3{v.x, v.y, v.z}; }
 RPT_HD float4 mk4(f3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 #endif
 
+// x / 255 for an integer 0 <= x <= 255, correctly rounded — the very value of the IEEE division the CPU path does
+// (src/asset.rs:266-273; all 256 inputs are checked in tests/test_wide_bvh_cpu.py) — without the division's
+// special-case machinery: one Newton step on x * (1/255).
+RPT_HD float unorm8(uint32_t x) {
+    const float xf = (float)x, r = 1.0f / 255.0f;
+    const float q = xf * r;
+    return fmaf(fmaf(-q, 255.0f, xf), r, q);
+}
+// size - 1 for a power-of-two image size (coordinates wrap with a mask), else 0
+RPT_HD uint32_t pow2_mask(uint32_t size) { return (size & (size - 1u)) == 0u ? size - 1u : 0u; }
+
 constexpr float kPi = 3.14159265358979323846f;
 constexpr float kEps = 0.001f;  // kernels/src/util.rs:5
 

@@ -27,6 +27,9 @@ struct LocalStack {
 
 extern "C" {
 
+// texel decoding of the shading kernels (dev/vec.cuh), for the exhaustive check against x / 255.0f
+float harness_unorm8(uint32_t x) { return rpt::unorm8(x); }
+
 // out_stats: [0] nodes, [1] max_depth, [2] inner_children, [3] leaf_children, [4] stack high-water
 int harness_wide_intersect(const RptPerVertexData* verts, uint32_t nverts, const uint32_t* tris, uint32_t ntris, const RptBVHNode* nodes,
                            uint32_t nnodes, const float* rays_o_d, uint32_t nrays, int any_hit, const float* max_t, uint32_t* out_hit,

@@ -49,6 +49,20 @@ def mae(a: np.ndarray, b: np.ndarray):
     return float(np.abs(a[~bad] - b[~bad]).mean()), int(bad.sum())
 
 
+def record_parity(case: str, **measured):
+    """Append one measured parity line (id mismatch fraction, MAE, ...) to gpurun_out/parity_report.jsonl, so the
+    numbers quoted in DESIGN.md / profiles/ come from the test run itself.  Best effort: never fails a test."""
+    import json
+
+    try:
+        out_dir = os.path.join(REPO, "gpurun_out")
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps({"case": case, **measured}) + "\n")
+    except OSError:
+        pass
+
+
 def synthetic_sky(width: int = 64, height: int = 32, seed: int = 7) -> np.ndarray:
     """Small deterministic lat-long HDR image (float4) with a bright disk."""
     rs = np.random.default_rng(seed)

@@ -72,6 +72,8 @@ def test_matches_oracle(scene, w, h, spp, nee, pipeline):
     assert mismatch <= ID_MISMATCH_BUDGET, f"primary-hit id mismatch fraction {mismatch}"
 
     err, bad = helpers.mae(c_out[:, :3] / spp, o_out[:, :3] / spp)
+    helpers.record_parity(f"{scene} {w}x{h} {spp}spp nee={nee} {'wavefront' if pipeline == capi.PIPELINE_WAVEFRONT else 'megakernel'}",
+                          id_mismatch=mismatch, mae=err, nan_pixels=bad)
     assert bad == int((~np.isfinite(o_out[:, :3]).all(axis=1)).sum()), "NaN pixels must match the CPU path's"
     assert err <= MAE_TOLERANCE, f"MAE {err}"
     assert c_ctr["paths"] == w * h * spp
@@ -117,6 +119,7 @@ def test_hdr_sky_and_rotated_camera():
         c_out, _, c_ids, _ = render_cuda(world, cfg, seeds, 16, pipeline, sky)
         assert float((c_ids != o_ids).mean()) <= ID_MISMATCH_BUDGET
         err, _ = helpers.mae(c_out[:, :3] / 16, o_out[:, :3] / 16)
+        helpers.record_parity(f"PBRTest 128x72 16spp HDR sky, rotated camera, pipeline {pipeline}", id_mismatch=float((c_ids != o_ids).mean()), mae=err)
         assert err <= MAE_TOLERANCE, err
 
 
@@ -131,6 +134,7 @@ def test_textured_atlas_and_normal_maps(pipeline):
     c_out, _, c_ids, _ = render_cuda(world, cfg, seeds, 16, pipeline)
     assert float((c_ids != o_ids).mean()) <= ID_MISMATCH_BUDGET
     err, _ = helpers.mae(c_out[:, :3] / 16, o_out[:, :3] / 16)
+    helpers.record_parity(f"PBRTest textured 160x88 16spp pipeline {pipeline}", id_mismatch=float((c_ids != o_ids).mean()), mae=err)
     assert err <= MAE_TOLERANCE, err
 
 
@@ -144,6 +148,7 @@ def test_breaktime_proxy_scene():
     c_out, _, c_ids, _ = render_cuda(world, cfg, seeds, 16, capi.PIPELINE_WAVEFRONT, sky)
     assert float((c_ids != o_ids).mean()) <= ID_MISMATCH_BUDGET
     err, bad = helpers.mae(c_out[:, :3] / 16, o_out[:, :3] / 16)
+    helpers.record_parity("BreakTime proxy (60k triangles) 160x90 16spp MIS, HDR sky", id_mismatch=float((c_ids != o_ids).mean()), mae=err, nan_pixels=bad)
     assert err <= MAE_TOLERANCE, err
 
 

@@ -88,3 +88,12 @@ def test_nan_and_degenerate_rays_miss(harness):
     wh, *_ = wide_intersect(harness, world, rays)
     np.testing.assert_array_equal(wh, oh)
     assert (wh == 0).all()
+
+
+def test_unorm8_is_the_ieee_division(harness):
+    """The shading kernels decode texels with one Newton step instead of a division; it must give exactly
+    `x as f32 / 255.0` (src/asset.rs:266-273) for every byte value."""
+    harness.harness_unorm8.restype = C.c_float
+    got = np.array([harness.harness_unorm8(C.c_uint32(x)) for x in range(256)], np.float32)
+    want = np.arange(256, dtype=np.float32) / np.float32(255.0)
+    np.testing.assert_array_equal(got, want)
