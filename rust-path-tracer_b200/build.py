@@ -67,12 +67,14 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
             # *_nofma.cu: the id-critical arithmetic (exact.cuh) — no FMA contraction, IEEE division and sqrt.
-            # wavefront_shade.cu: shading is held to a radiance tolerance, not to bit identity, so division and
-            # sqrt use the 2-ulp approximate forms (no special-case subroutine: ncu showed a third of the
-            # kernel's instructions inside it); transcendentals stay the accurate ones.
+            # wavefront_shade.cu: shading is held to a radiance tolerance, not to bit identity.  It is built without
+            # FMA contraction too (the kernel is HBM-bound, the extra FMUL/FADD are free, and on chaotic scenes every
+            # ulp of agreement with the CPU path counts: MAE 3.3e-4 -> 5.7e-5 on the BreakTime proxy), but with the
+            # 2-ulp approximate division and sqrt (IEEE ones cost +75 % shade time: a third of the instructions sat in
+            # their special-case subroutine); the specular lobe and the HDR sky lookup ask for IEEE explicitly.
             extra = ["-fmad=false"] if src.endswith("_nofma.cu") else []
             if os.path.basename(src) == "wavefront_shade.cu":
-                extra += ["-prec-div=false", "-prec-sqrt=false"]
+                extra += ["-fmad=false", "-prec-div=false", "-prec-sqrt=false"]
             cmd = [nvcc, *ARCH_FLAGS, *NVCC_FLAGS, *extra, "-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-x", "cu", "-c", src, "-o", obj]
             jobs.append((src, cmd))
 

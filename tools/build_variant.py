@@ -1,0 +1,19 @@
+"""Scratch: build librpt variants with different flags for wavefront_shade.cu (A/B runs via RPT_B200_LIBRARY).
+usage: python tools/build_variant.py NAME FLAG [FLAG ...]   ->  rust-path-tracer_b200/_build/variants/librpt_NAME.so"""
+import os, subprocess, sys
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from rust_path_tracer_b200 import build as b
+
+name, flags = sys.argv[1], sys.argv[2:]
+b.build_library()
+nvcc = b._nvcc()
+out = os.path.join(b.OUT_DIR, "variants"); os.makedirs(out, exist_ok=True)
+objs = [os.path.join(b.OUT_DIR, os.path.basename(s) + ".o") for s in b._sources()]
+src = os.path.join(b.CSRC, "wavefront_shade.cu")
+obj = os.path.join(out, f"shade_{name}.o")
+subprocess.run([nvcc, *b.ARCH_FLAGS, *b.NVCC_FLAGS, *flags, "-I", os.path.join(b.REPO_DIR, "include"), "-I", b.CSRC, "-x", "cu", "-c", src, "-o", obj], check=True, capture_output=True)
+lib = os.path.join(out, f"librpt_{name}.so")
+others = [o for o in objs if not o.endswith("wavefront_shade.cu.o")]
+subprocess.run([nvcc, *b.ARCH_FLAGS, "-shared", "-ccbin", b.HOST_CXX, "-Xcompiler", "-fPIC", "-o", lib, obj, *others, "-ldl", "-lpthread", "-cudart", "static"], check=True, capture_output=True)
+print(lib)
