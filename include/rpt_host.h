@@ -8,6 +8,8 @@
  *                                  src/light_pick.rs:13-122 (called from src/asset.rs:201-202)
  *   rpt_pack_per_vertex         <- the PerVertexData packing loop, src/asset.rs:205-215
  *   rpt_make_rng_seeds          <- blue-noise / uniform seed tables, src/trace.rs:149-160, 245-256
+ *   rpt_atlas_rects / rpt_atlas_pack / rpt_decode_albedo_gamma
+ *                               <- pack_textures, src/atlas.rs:26-92, and the albedo decode of src/asset.rs:140-147
  *   rpt_tile_partition_pixels   <- (new) the tile split used by rpt_set_tile_partition
  *   rpt_camera_matrix           <- Mat3::from_rotation_y(ry) * Mat3::from_rotation_x(rx),
  *                                  kernels/src/lib.rs:50 (host libm keeps primary rays bit-exact)
@@ -16,6 +18,8 @@
  */
 #ifndef RPT_HOST_H
 #define RPT_HOST_H
+
+#include <stddef.h>
 
 #include "rpt_shared_structs.h"
 
@@ -45,6 +49,15 @@ int rpt_pack_per_vertex(const float* vertices, const float* normals, const float
  * (blue-noise mode); blue == NULL: x = splitmix-style uniform from `uniform_seed`, y = 0. */
 int rpt_make_rng_seeds(const uint8_t* blue_r8, uint32_t bw, uint32_t bh, uint32_t width, uint32_t height,
                        uint64_t uniform_seed, uint32_t* seeds_xy_out);
+
+/* Texture atlas (src/atlas.rs).  Leaf rectangles (x, y, w, h) of `ntextures` textures in packing order. */
+int rpt_atlas_rects(uint32_t ntextures, uint32_t atlas_w, uint32_t atlas_h, uint32_t* rects_xywh_out);
+/* Pack RGBA8 textures (row-major, widths[i] x heights[i]) into a zeroed atlas_w x atlas_h RGBA8 atlas: Lanczos3
+ * resize to the leaf when the size differs, vertical flip, copy.  sts_out: ntextures x float[4] (x/W, y/W, w/W, h/H). */
+int rpt_atlas_pack(const uint8_t* const* textures_rgba8, const uint32_t* widths, const uint32_t* heights, uint32_t ntextures,
+                   uint32_t atlas_w, uint32_t atlas_h, uint8_t* atlas_rgba8_out, float* sts_out);
+/* `((p / 255).powf(2.2) * 255) as u8` on RGB, alpha -> 255 (albedo textures, before packing). */
+int rpt_decode_albedo_gamma(const uint8_t* rgba8_in, size_t npixels, uint8_t* rgba8_out);
 
 /* Multi-GPU tile split: pixel indices (row-major y*width+x) of the 32x32 tiles t
  * with t % tile_count == tile_rank, tile by tile.  pixels_out may be NULL to query the count. */

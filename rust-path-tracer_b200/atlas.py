@@ -1,59 +1,48 @@
-"""Texture atlas packing — host-side input producer, restating src/atlas.rs and
-the texture part of the material loop in src/asset.rs:135-192.
+"""Texture atlas packing — host-side input producer: a thin binding of the C++ restatement
+of src/atlas.rs and the texture part of src/asset.rs:135-192 (csrc/atlas_build.cpp, include/rpt_host.h).
 
 * quadtree split of the atlas until there are more leaves than textures, leaves sorted by
   descending width (stable) and truncated (src/atlas.rs:26-69);
-* every texture resized to its leaf, flipped vertically, copied in (src/atlas.rs:71-87);
+* every texture resized to its leaf (Lanczos3), flipped vertically, copied in (src/atlas.rs:71-87);
 * the rect handed to the kernel is (x/W, y/W, w/W, h/H) — the y offset really is divided by the
   atlas WIDTH (src/atlas.rs:16-23; harmless for the square atlas the reference uses);
 * albedo textures are gamma-2.2 decoded in 8 bits before packing (src/asset.rs:140-147);
 * per material the order is albedo, metallic, roughness, normals (src/asset.rs:138-163,179-192).
-
-The reference resizes with fast_image_resize's Lanczos3; here PIL's LANCZOS is used when a texture
-is not already leaf-sized (not bit-identical; the synthetic scenes of this repo generate textures
-at leaf size, so no resampling happens on the paths that are parity-tested).
 """
 from __future__ import annotations
 
-from collections import deque
+import ctypes as C
 
 import numpy as np
 
+from . import capi
+
 
 def packing_rects(ntextures: int, atlas_w: int, atlas_h: int):
-    queue = deque([(0, 0, atlas_w, atlas_h)])
-    while len(queue) <= ntextures:
-        x, y, w, h = queue.popleft()
-        hw, hh = w // 2, h // 2
-        queue.extend([(x, y, hw, hh), (x + hw, y, hw, hh), (x, y + hh, hw, hh), (x + hw, y + hh, hw, hh)])
-    leaves = sorted(queue, key=lambda r: -r[2])  # stable, like slice::sort_by
-    return leaves[:ntextures]
+    rects = np.zeros((ntextures, 4), np.uint32)
+    capi.check(capi.lib().rpt_atlas_rects(C.c_uint32(ntextures), C.c_uint32(atlas_w), C.c_uint32(atlas_h), capi.ptr(rects)), "rpt_atlas_rects")
+    return [tuple(int(v) for v in r) for r in rects]
 
 
 def pack_textures(textures, atlas_w: int = 4096, atlas_h: int = 4096):
     """textures: list of (H, W, 4) uint8.  Returns (atlas (atlas_h, atlas_w, 4) uint8, list of rects f32[4])."""
-    atlas = np.zeros((atlas_h, atlas_w, 4), np.uint8)
-    rects = packing_rects(len(textures), atlas_w, atlas_h) if textures else []
-    sts = []
-    for tex, (x, y, w, h) in zip(textures, rects):
-        tex = np.ascontiguousarray(tex, np.uint8)
-        if tex.shape[0] != h or tex.shape[1] != w:
-            from PIL import Image
-
-            tex = np.asarray(Image.fromarray(tex, "RGBA").resize((w, h), Image.LANCZOS), np.uint8)
-        atlas[y:y + h, x:x + w] = tex[::-1]  # flipv
-        f = np.float32
-        sts.append(np.array([f(x) / f(atlas_w), f(y) / f(atlas_w), f(w) / f(atlas_w), f(h) / f(atlas_h)], np.float32))
-    return atlas, sts
+    texs = [np.ascontiguousarray(t, np.uint8) for t in textures]
+    n = len(texs)
+    atlas = np.empty((atlas_h, atlas_w, 4), np.uint8)
+    sts = np.zeros((n, 4), np.float32)
+    pointers = (C.c_void_p * max(n, 1))(*[t.ctypes.data for t in texs])
+    widths = np.array([t.shape[1] for t in texs], np.uint32)
+    heights = np.array([t.shape[0] for t in texs], np.uint32)
+    capi.check(capi.lib().rpt_atlas_pack(pointers, capi.ptr(widths), capi.ptr(heights), C.c_uint32(n), C.c_uint32(atlas_w), C.c_uint32(atlas_h),
+                                         capi.ptr(atlas), capi.ptr(sts)), "rpt_atlas_pack")
+    return atlas, [sts[i].copy() for i in range(n)]
 
 
 def decode_albedo_gamma(tex: np.ndarray) -> np.ndarray:
     """`((p / 255).powf(2.2) * 255) as u8` on RGB; the result is an RGB image (alpha dropped -> 255)."""
-    rgb = tex[..., :3].astype(np.float32) / np.float32(255.0)
-    lin = np.power(rgb, np.float32(2.2), dtype=np.float32) * np.float32(255.0)
-    out = np.empty(tex.shape[:2] + (4,), np.uint8)
-    out[..., :3] = np.clip(np.floor(lin), 0, 255).astype(np.uint8)
-    out[..., 3] = 255
+    tex = np.ascontiguousarray(tex, np.uint8)
+    out = np.empty_like(tex)
+    capi.check(capi.lib().rpt_decode_albedo_gamma(capi.ptr(tex), C.c_size_t(tex.shape[0] * tex.shape[1]), capi.ptr(out)), "rpt_decode_albedo_gamma")
     return out
 
 

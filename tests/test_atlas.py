@@ -37,3 +37,32 @@ def test_textured_scene_traces_and_uses_the_atlas():
     a, *_ = om.trace(cfg, om.OracleScene(w), helpers.seeds(64, 36), 4)
     b, *_ = om.trace(cfg, om.OracleScene(plain), helpers.seeds(64, 36), 4)
     assert np.isfinite(a).all() and np.abs(a[:, :3] - b[:, :3]).mean() > 1e-3  # textures change the image
+
+
+def test_lanczos_resize_matches_the_published_algorithm():
+    """A texture that is not leaf-sized goes through the Lanczos3 convolution (src/atlas.rs:71-83, fast_image_resize);
+    the restatement follows Pillow's published resampling, so Pillow is the checker here (test-only dependency)."""
+    from PIL import Image
+
+    rs = np.random.default_rng(3)
+    for shape in ((96, 160), (300, 200), (256, 256), (700, 513)):
+        tex = rs.integers(0, 256, shape + (4,), dtype=np.uint8)
+        tex[: shape[0] // 2] //= 4  # some structure, not only noise
+        atlas, sts = atlas_mod.pack_textures([tex], 512, 512)
+        # channel by channel: Pillow premultiplies alpha when it resizes an RGBA image, the reference's resizer does not
+        want = np.stack([np.asarray(Image.fromarray(tex[..., c], "L").resize((256, 256), Image.LANCZOS), np.uint8) for c in range(4)], axis=2)[::-1]
+        got = atlas[:256, :256]
+        diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+        assert diff.max() <= 1, (shape, int(diff.max()))  # same taps; rounding of the 8-bit intermediate may differ by 1
+        assert (atlas[256:] == 0).all() and (atlas[:, 256:] == 0).all()
+        np.testing.assert_array_equal(sts[0], np.array([0, 0, 0.5, 0.5], np.float32))
+
+
+def test_atlas_errors_are_status_codes():
+    import ctypes as C
+
+    from rust_path_tracer_b200 import capi
+
+    assert capi.lib().rpt_atlas_rects(C.c_uint32(1), C.c_uint32(0), C.c_uint32(16), None) == capi.ERR_INVALID_ARGUMENT
+    rects = np.zeros((100, 4), np.uint32)  # 100 textures cannot fit a 4x4 atlas: leaves would be empty
+    assert capi.lib().rpt_atlas_rects(C.c_uint32(100), C.c_uint32(4), C.c_uint32(4), capi.ptr(rects)) == capi.ERR_UNSUPPORTED
