@@ -6,17 +6,17 @@
 // Built with -fmad=false: ray generation and the ray/triangle test evaluate the reference's fp32
 // operations in its order (dev/exact.cuh), which is what makes primary-hit ids bit-exact.
 //
-// All three are persistent kernels: the grid is a fixed multiple of the SM count and warps
-// stride over the queue, whose length lives in device memory (WaveCtl) so the host never has to
-// read it back.  Each lane keeps its traversal stack in a per-warp shared-memory slab
-// (stack[depth][lane]: conflict-free 8-byte accesses), and queue appends are warp-aggregated:
-// one atomicAdd per warp, slots handed out by ballot + popc.
+// All three are persistent kernels: the grid is a fixed multiple of the SM count and warps pull work
+// from the queue, whose length lives in device memory (WaveCtl) so the host never has to read it
+// back.  Each lane keeps its traversal stack in a per-warp shared-memory slab (stack[depth][lane]:
+// conflict-free 8-byte accesses); rays are handed out with one atomicAdd per warp (ballot + popc),
+// and the output queues are built afterwards by the order-preserving compaction kernels below.
 #include "device_scene.h"
 #include "wide_bvh.h"
 
 namespace rpt {
 
-constexpr int kTraceBlock = 128;  // 4 warps; 24 KB of stack slabs per block
+constexpr int kTraceBlock = 128;  // 4 warps; 16 KB of stack slabs + the 2 KB permutation table per block
 constexpr int kTraceWarps = kTraceBlock / 32;
 
 struct SmemStack {
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(FrameParams f, WaveSta
 //            (or miss) record goes to s.hit[slot]; wf_compact_kernel then splits the slots into
 //            q_hit / q_miss IN QUEUE ORDER, so the shading stages read path state coalesced
 //            although rays finish in any order here.
-//   ANY:     items are shadow-queue entries; an unoccluded ray adds its contribution to rad[slot].
+//   ANY:     items are the shadow rays listed in q_shadow; an unoccluded ray adds its contribution to rad[slot].
 // Lanes pull rays one at a time from a device-side cursor: when a lane's ray terminates it waits
 // only until the warp's live-lane count drops below `refill_below`, then every idle lane is handed
 // a new ray (ray refill keeps the warp full although rays need very different numbers of steps).
