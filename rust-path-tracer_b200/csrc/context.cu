@@ -98,7 +98,7 @@ struct rpt_context {
     uint32_t wave_slots = kDefaultWaveSlots;
     // trace-kernel tunables (defaults chosen on B200; RPT_* env vars override for sweeps)
     bool log_queues = false;  // RPT_LOG_QUEUES=1: print every bounce's queue lengths (syncs; for reading ncu captures)
-    int trace_blocks_per_sm = 8;
+    int trace_blocks_per_sm = 9;  // = the __launch_bounds__ of wf_trace_kernel: 56 registers, 36 warps per SM
     int refill_below = 20;
 
     // scene, reference layouts (megakernel arm)

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(FrameParams f, WaveSta
 constexpr uint32_t kMissRecord = 0xFFFFFFFFu;  // hit[].y of a ray that hit nothing (triangle indices are < 2^31)
 
 template <bool NEAREST>
-__global__ void __launch_bounds__(kTraceBlock, 8) wf_trace_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
+__global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
                                                                int refill_below) {
     __shared__ uint2 slabs[kTraceWarps][kWideStackCapacity][32];
     __shared__ uint8_t perm_table[8 * 256];
