@@ -239,7 +239,7 @@ void launch_wf_miss_procedural(const WaveLaunch& l, const FrameParams& f, const 
     wf_miss_procedural_kernel<<<l.grid * 8, 128, 0, l.stream>>>(f, s);
 }
 void launch_wf_accumulate(const WaveLaunch& l, const WaveState& s, const WaveDesc& d, uint2* rng, float4* output) {
-    wf_accumulate_kernel<<<l.grid * 2, 256, 0, l.stream>>>(s, d, rng, output);
+    wf_accumulate_kernel<<<l.grid * 8, 256, 0, l.stream>>>(s, d, rng, output);
 }
 void launch_normalize(const float4* output, float* rgb, uint32_t npixels, float samples, cudaStream_t stream) {
     normalize_kernel<<<(npixels + 255) / 256, 256, 0, stream>>>(output, rgb, npixels, samples);

@@ -274,21 +274,21 @@ __global__ void wf_export_primary_hits_kernel(WideScene bvh, WaveState s, WaveDe
 }
 
 void launch_wf_generate(const WaveLaunch& l, const FrameParams& f, const WaveState& s, const WaveDesc& d, const uint2* rng) {
-    wf_generate_kernel<<<l.grid * 2, 256, 0, l.stream>>>(f, s, d, rng);
+    wf_generate_kernel<<<l.grid * 8, 256, 0, l.stream>>>(f, s, d, rng);
 }
 void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, int in_queue, bool identity_queue, uint32_t n_identity) {
     wf_trace_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below);
-    wf_compact_kernel<<<l.grid * 2, kCompactBlock, 0, l.stream>>>(s, in_queue, identity_queue, n_identity);
+    wf_compact_kernel<<<l.grid * 8, kCompactBlock, 0, l.stream>>>(s, in_queue, identity_queue, n_identity);
 }
 void launch_wf_compact_shaded(const WaveLaunch& l, const WaveState& s, int out_queue) {
-    wf_compact_shaded_kernel<<<l.grid * 2, kCompactBlock, 0, l.stream>>>(s, out_queue);
+    wf_compact_shaded_kernel<<<l.grid * 8, kCompactBlock, 0, l.stream>>>(s, out_queue);
 }
 void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState& s) {
     wf_trace_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below);
 }
 void launch_wf_export_primary(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, const WaveDesc& d, uint32_t* ids) {
     wf_export_primary_kernel<<<(d.npix + 255) / 256, 256, 0, l.stream>>>(bvh, s, d, ids);
-    wf_export_primary_hits_kernel<<<l.grid * 2, 256, 0, l.stream>>>(bvh, s, d, ids);
+    wf_export_primary_hits_kernel<<<l.grid * 8, 256, 0, l.stream>>>(bvh, s, d, ids);
 }
 
 }  // namespace rpt
