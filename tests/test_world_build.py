@@ -161,3 +161,30 @@ def test_blue_noise_seeds():
     px = tile[5, 7]
     expect = min(int(np.float32(np.float32(px) / np.float32(255.0)) * np.float32(4294967296.0)), 0xFFFFFFFF)
     assert y[5, 7] == expect
+
+
+def test_parallel_bvh_build_is_identical_to_the_sequential_one(monkeypatch):
+    """The builder forks the big subtrees near the root into tasks and splices their local node arrays; nodes,
+    their order and the permutation of the index buffer must not depend on the thread count."""
+    import ctypes as C
+
+    from rust_path_tracer_b200 import capi
+
+    scene = helpers.proxy_world.__wrapped__  # noqa: F841  (keep the cached world out of this: build from raw buffers)
+    rs = np.random.default_rng(5)
+    nt = 40000
+    centers = rs.random((nt, 3)).astype(np.float32) * np.float32(20.0)
+    verts = np.zeros((nt * 3, 4), np.float32)
+    verts[:, :3] = np.repeat(centers, 3, axis=0) + rs.normal(0, 0.05, (nt * 3, 3)).astype(np.float32)
+    tris0 = np.zeros((nt, 4), np.uint32)
+    tris0[:, :3] = np.arange(nt * 3, dtype=np.uint32).reshape(nt, 3)
+    results = []
+    for threads in ("1", "2", "7", "16"):
+        monkeypatch.setenv("RPT_BUILD_THREADS", threads)
+        tris = tris0.copy()
+        nodes = np.zeros(2 * nt - 1, capi.BVH_NODE_DTYPE)
+        n = C.c_uint32(0)
+        capi.check(capi.lib().rpt_build_bvh(capi.ptr(verts), C.c_uint32(len(verts)), capi.ptr(tris), C.c_uint32(nt), C.c_uint32(128), capi.ptr(nodes),
+                                            C.byref(n)), "rpt_build_bvh")
+        results.append((nodes[: n.value].tobytes(), tris.tobytes()))
+    assert all(r == results[0] for r in results[1:])
