@@ -143,6 +143,20 @@ struct rpt_context {
 
     uint64_t kernel_launches = 0;
     uint64_t mega_paths = 0;
+
+    // CUDA graphs of whole waves.  A wave is a fixed sequence of ~30 launches whose arguments only depend on the
+    // scene, the config, the buffers and the wave's shape, so it is captured once and replayed: one launch per
+    // wave instead of thirty, which is what bounds small frames (a 128x128 x 32 spp batch is ~150 us of GPU work).
+    // `graph_epoch` moves whenever something baked into the captured arguments changes.
+    struct WaveGraph { WaveDesc desc; uint64_t epoch; cudaGraphExec_t exec; uint64_t launches; };
+    std::vector<WaveGraph> wave_graphs;
+    uint64_t graph_epoch = 0;
+    bool use_graphs = true;  // RPT_GRAPHS=0 turns them off
+    void drop_graphs() {
+        for (auto& g : wave_graphs) cudaGraphExecDestroy(g.exec);
+        wave_graphs.clear();
+        ++graph_epoch;
+    }
     bool stage_timing = false;
     struct StageEvent { int stage; cudaEvent_t e0, e1; };
     std::vector<StageEvent> stage_events;
@@ -269,6 +283,7 @@ WaveState wave_state(rpt_context* c) {
 
 int ensure_wave(rpt_context* c, uint32_t slots) {
     if (slots <= c->wave_capacity) return RPT_OK;
+    c->drop_graphs();  // the path-state buffers move
     RPT_CUDA(c, c->w_ray_o.alloc(slots)); RPT_CUDA(c, c->w_ray_d.alloc(slots)); RPT_CUDA(c, c->w_thr.alloc(slots));
     RPT_CUDA(c, c->w_rad.alloc(slots));
     RPT_CUDA(c, c->w_sh_o.alloc(slots)); RPT_CUDA(c, c->w_sh_d.alloc(slots)); RPT_CUDA(c, c->w_sh_c.alloc(slots));
@@ -348,6 +363,35 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
     return c->cuda(cudaGetLastError(), "wavefront launch");
 }
 
+// run_wave through a captured graph (captured on first use of this wave shape).
+int run_wave_graphed(rpt_context* c, const WaveDesc& d) {
+    if (!c->use_graphs || c->stage_timing || c->log_queues) return run_wave(c, d, false, nullptr);
+    for (auto& g : c->wave_graphs)
+        if (g.epoch == c->graph_epoch && g.desc.pix_base == d.pix_base && g.desc.npix == d.npix && g.desc.k_samples == d.k_samples &&
+            g.desc.pixel_map == d.pixel_map) {
+            c->kernel_launches += g.launches;
+            return c->cuda(cudaGraphLaunch(g.exec, c->stream), "cudaGraphLaunch");
+        }
+    if (c->wave_graphs.size() >= 16) c->drop_graphs();  // (a frame is a handful of wave shapes)
+    const uint64_t before = c->kernel_launches;
+    RPT_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int status = run_wave(c, d, false, nullptr);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t end = cudaStreamEndCapture(c->stream, &graph);
+    if (status != RPT_OK || end != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        c->kernel_launches = before;
+        return status != RPT_OK ? status : c->cuda(end != cudaSuccess ? end : cudaErrorUnknown, "wave graph capture");
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t inst = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess) { c->kernel_launches = before; return c->cuda(inst, "cudaGraphInstantiate"); }
+    c->wave_graphs.push_back({d, c->graph_epoch, exec, c->kernel_launches - before});
+    return c->cuda(cudaGraphLaunch(exec, c->stream), "cudaGraphLaunch");
+}
+
 template <class Fn>
 int for_each_wave(rpt_context* c, uint32_t n_samples, Fn&& fn) {
     const uint32_t total = c->tile_count > 1 ? c->pixel_map_len : c->npixels();
@@ -405,6 +449,7 @@ extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
     if (const char* v = getenv("RPT_TRACE_BLOCKS_PER_SM")) c->trace_blocks_per_sm = std::max(1, atoi(v));
     if (const char* v = getenv("RPT_REFILL_BELOW")) c->refill_below = atoi(v);
     if (const char* v = getenv("RPT_LOG_QUEUES")) c->log_queues = atoi(v) != 0;
+    if (const char* v = getenv("RPT_GRAPHS")) c->use_graphs = atoi(v) != 0;
     if (const char* v = getenv("RPT_WAVE_SLOTS")) c->wave_slots = (uint32_t)std::max(1024, atoi(v));
     *out_ctx = c;
     return RPT_OK;
@@ -414,6 +459,7 @@ extern "C" int rpt_destroy(rpt_context* c) {
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    c->drop_graphs();
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     for (auto& ev : c->timed) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     c->drain_stage_events();
@@ -460,6 +506,7 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
         if (triangles[4 * t + 3] >= nmaterials) return c->fail(RPT_ERR_INVALID_ARGUMENT, "triangle %zu references material %u of %u", t, triangles[4 * t + 3], nmaterials);
     RPT_TRY(bind_device(c));
     c->has_world = false;
+    c->drop_graphs();
 
     // ---- private re-layout (host side, once per scene)
     WideBvh wide;
@@ -587,6 +634,7 @@ extern "C" int rpt_set_config(rpt_context* c, const RptTracingConfig* cfg) {
         return c->fail(RPT_ERR_RNG_DIMENSIONS, "config can consume %u R-sequence dimensions per path; the reference's table has 31 (kernels/src/rng.rs:19-27)", dims);
     RPT_TRY(bind_device(c));
     const bool resized = !c->has_config || cfg->width != c->config.width || cfg->height != c->config.height;
+    if (!c->has_config || std::memcmp(&c->config, cfg, sizeof *cfg) != 0) c->drop_graphs();  // the config is baked into the launches
     c->config = *cfg;
     c->has_config = true;
     float m[9];
@@ -650,6 +698,7 @@ extern "C" int rpt_set_tile_partition(rpt_context* c, uint32_t tile_rank, uint32
     RPT_TRY(bind_device(c));
     c->tile_rank = tile_rank;
     c->tile_count = tile_count;
+    c->drop_graphs();
     return rebuild_pixel_map(c);
 }
 
@@ -694,7 +743,7 @@ extern "C" int rpt_enqueue(rpt_context* c, uint32_t n_samples) {
         // the megakernel counts its rays on the device; finished paths are counted here
         if (status == RPT_OK) c->mega_paths += (uint64_t)(c->tile_count > 1 ? c->pixel_map_len : c->npixels()) * n_samples;
     } else {
-        status = for_each_wave(c, n_samples, [&](const WaveDesc& d) { return run_wave(c, d, false, nullptr); });
+        status = for_each_wave(c, n_samples, [&](const WaveDesc& d) { return run_wave_graphed(c, d); });
     }
     cudaEventRecord(e1, c->stream);
     c->timed.emplace_back(e0, e1);
