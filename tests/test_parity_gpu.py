@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star):
   * accumulated radiance: mean absolute error <= 1e-3 at matched spp and sample indices;
   * FurnaceTest stays energy conserving (the reference's own known answer, tests/correctness_tests.rs).
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -400,3 +402,25 @@ def test_wave_graphs_follow_state_changes():
         r.set_config(cfg_c); r.write_rng(helpers.seeds(80, 48))  # other frame size: buffers are reallocated
         r.enqueue(4)
         np.testing.assert_array_equal(r.read_output(), fresh(furnace, cfg_c, 4))
+
+
+def test_page_locked_staging_buffers():
+    """rpt_host_alloc memory is an ordinary host pointer to every call: same results as pageable numpy arrays."""
+    world = helpers.world("VeachMIS")
+    w, h = 128, 72
+    cfg = helpers.config(w, h, 1)
+    seeds = helpers.seeds(w, h)
+    pinned_seeds = capi.pinned_empty(seeds.shape, np.uint32)
+    pinned_seeds[...] = seeds
+    frame = capi.pinned_empty(w * h * 3, np.float32)
+    with Renderer(0) as r:
+        r.upload_world(world); r.set_config(cfg); r.write_rng(seeds)
+        r.enqueue(4)
+        want = r.read_framebuffer(4.0)
+        r.write_rng(pinned_seeds); r.write_output(None)
+        r.enqueue(4)
+        r.read_framebuffer(4.0, frame)
+    np.testing.assert_array_equal(frame, want)
+    del frame, pinned_seeds  # frees the blocks (rpt_host_free) without complaint
+    assert capi.lib().rpt_host_alloc(C.c_size_t(0), C.byref(C.c_void_p())) == capi.ERR_INVALID_ARGUMENT
+    assert capi.lib().rpt_host_free(None) == capi.ERR_INVALID_ARGUMENT
