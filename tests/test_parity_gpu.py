@@ -424,3 +424,21 @@ def test_page_locked_staging_buffers():
     del frame, pinned_seeds  # frees the blocks (rpt_host_free) without complaint
     assert capi.lib().rpt_host_alloc(C.c_size_t(0), C.byref(C.c_void_p())) == capi.ERR_INVALID_ARGUMENT
     assert capi.lib().rpt_host_free(None) == capi.ERR_INVALID_ARGUMENT
+
+
+def test_more_materials_than_fit_in_shared_memory():
+    """The shade kernel stages up to 64 materials in shared memory and reads larger tables from global memory:
+    a copy of DarkCornell in which every triangle owns a private copy of its material must render bit-identically."""
+    import dataclasses
+
+    base = helpers.world("DarkCornell")
+    tris = base.index_buffer.copy()
+    mats = base.material_data_buffer[tris[:, 3]].copy()  # one material per triangle: 184 > 64
+    tris[:, 3] = np.arange(len(tris), dtype=np.uint32)
+    many = dataclasses.replace(base, index_buffer=tris, material_data_buffer=mats)
+    assert len(many.material_data_buffer) > 64
+    cfg = helpers.config(96, 64, 1)
+    seeds = helpers.seeds(96, 64)
+    want, *_ = render_cuda(base, cfg, seeds, 8, capi.PIPELINE_WAVEFRONT)
+    got, *_ = render_cuda(many, cfg, seeds, 8, capi.PIPELINE_WAVEFRONT)
+    np.testing.assert_array_equal(got, want)
