@@ -20,6 +20,9 @@ committed fixtures under tests/golden/scenes, sample indices from the blue-noise
 N > 1 (torchrun, one rank per GPU): every rank renders the full frame over its own sample-index
 range (rank r starts at sample r * K * spp) — per-GPU work is fixed, so scaling is "weak" — and the
 per-GPU accumulators are combined once, inside the timed region, by ncclReduce over NVLink.
+`--partition tiles` (configs[4]: 4K frame tiled over the GPUs) gives every rank the 32x32 tiles t with
+t % N == rank at the same sample indices instead — total work is fixed, scaling is "strong", and the reduce
+adds disjoint tiles (bit-identical to one GPU).
 
 Keys beyond the base contract: `mrays_per_s`, `roofline` (extend kernel), `cpu_baseline`
 (oracle on the host cores), `e2e` (same metric through the C ABI with host buffers in the timed
@@ -51,6 +54,8 @@ WORKLOADS = {
     "pbr-textured": ("PBRTest+procedural textures", 1920, 1080, 0, 16, "configs[2] PBRTest.glb 1920x1080 with a synthetic 4096^2 metallic/roughness/albedo/normal atlas"),
     "breaktime": ("BreakTime PROXY (synthetic ~1M-triangle textured interior, HDR sky)", 1920, 1080, 1, 16,
                   "north-star scene BreakTime.glb 1920x1080 — asset absent, LABELLED SYNTHETIC PROXY"),
+    "breaktime-4k": ("BreakTime PROXY (synthetic ~1M-triangle textured interior, HDR sky)", 3840, 2160, 1, 4,
+                     "configs[4] BreakTime.glb 3840x2160, HDR sky — asset absent, LABELLED SYNTHETIC PROXY (use --partition tiles)"),
 }
 
 
@@ -133,7 +138,7 @@ def load_workload(name):
 
         baked, atlas = textured_pbr_variant(BakedScene.load(os.path.join(REPO, "tests", "golden", "scenes", "PBRTest.npz")))
         world = World.from_baked(baked, atlas=atlas)
-    elif name == "breaktime":
+    elif name in ("breaktime", "breaktime-4k"):
         from rust_path_tracer_b200.scenes import breaktime_proxy, synthetic_hdr_sky
 
         baked, atlas = breaktime_proxy()
@@ -237,7 +242,11 @@ def run_b200(args):
         r.set_wave_slots(args.wave_slots)
     # sample-index-range split: rank r owns samples [r*K*spp, (r+1)*K*spp) (+ warm-up samples first)
     seeds = seeds0.copy()
-    seeds[:, 0] += np.uint32(rank * (args.steps + args.warmup) * spp)
+    tiles = args.partition == "tiles" and world_size > 1
+    if tiles:
+        r.set_tile_partition(rank, world_size)
+    else:
+        seeds[:, 0] += np.uint32(rank * (args.steps + args.warmup) * spp)
     r.write_rng(seeds)
     if dist is not None:
         from rust_path_tracer_b200.dist import init_comm
@@ -278,11 +287,12 @@ def run_b200(args):
 
     line = {
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * job_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": 1e3 * job_s / args.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": label, "scene": scene, "width": cfg.width, "height": cfg.height,
                    "nee": cfg.nee, "min_bounces": cfg.min_bounces, "max_bounces": cfg.max_bounces, "spp_per_step": spp,
-                   "pipeline": args.pipeline, "partition": f"sample-index range x{world_size} + ncclReduce" if world_size > 1 else "single GPU",
+                   "pipeline": args.pipeline,
+                   "partition": (f"32x32 tiles round-robin x{world_size} + ncclReduce" if tiles else f"sample-index range x{world_size} + ncclReduce") if world_size > 1 else "single GPU",
                    "l2": "working set per step (path state %.0f MB) exceeds the 126 MB L2" % (144.0 * min(npix * spp, args.wave_slots or (1 << 24)) / 1e6)},
         "mrays_per_s": total_rays / job_s / 1e6,
         "wall_ms_per_step": 1e3 * wall_s / args.steps,
@@ -373,7 +383,7 @@ def run_b200(args):
     e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
-    line["e2e"] = {"value": npix * spp * args.steps * world_size / float(e2e[0]) / 1e6, "unit": "Mpaths/s",
+    line["e2e"] = {"value": npix * spp * args.steps * (1 if tiles else world_size) / float(e2e[0]) / 1e6, "unit": "Mpaths/s",
                    "h2d_bytes_per_step": 80 + 8 * npix, "d2h_bytes_per_step": 12 * npix,
                    "what": "per step: rpt_set_config + rpt_write_rng (pinned host seeds) + rpt_enqueue + rpt_read_framebuffer (pinned host RGB)"}
     if not np.isfinite(fb).all():
@@ -396,6 +406,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="breaktime")
     ap.add_argument("--pipeline", choices=["wavefront", "megakernel"], default="wavefront")
+    ap.add_argument("--partition", choices=["samples", "tiles"], default="samples", help="how N > 1 GPUs share the frame")
     ap.add_argument("--spp", type=int, default=0, help="samples per step (default: the workload's)")
     ap.add_argument("--wave-slots", type=int, default=0)
     ap.add_argument("--quick", action="store_true", help="skip the roofline and cpu_baseline legs")
