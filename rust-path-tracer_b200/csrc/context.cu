@@ -117,7 +117,6 @@ struct rpt_context {
     DevBuf<LightRecord> d_light_records;
     uint32_t nbins = 0;
     bool has_world = false;
-    bool scene_closed_hint = false;
 
     // render state
     RptTracingConfig config{};
