@@ -167,6 +167,9 @@ struct WideCursor {
     uint32_t next;
     uint2 ngroup, tgroup;
     uint32_t tvalid;
+#if !defined(__CUDACC__)
+    uint32_t last_child_hits = 0;  // host builds only (tests / statistics): child bits of the last visit
+#endif
 
     RPT_D void begin(f3 ro, f3 rd, float max_t_) {
         ray = make_wide_ray(ro, rd);
@@ -227,6 +230,9 @@ struct WideCursor {
 
         // ---- the node after this one: its nearest hit child, else the nearest pending sibling, else the stack
         const uint32_t child_hits = stack.permute(ray.oct_inv, (h >> 24) & imask) << 24;
+#if !defined(__CUDACC__)
+        last_child_hits = child_hits;
+#endif
         if (child_hits != 0u) {
             if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
             ngroup = make_uint2(n1.x, child_hits | imask);

@@ -27,6 +27,31 @@ struct LocalStack {
 
 extern "C" {
 
+// Traversal statistics of nearest-hit rays (tools / experiments): [0] node visits, [1] visits that hit no child and no
+// triangle, [2] triangle tests, [3] rays
+int harness_wide_stats(const RptPerVertexData* verts, uint32_t nverts, const uint32_t* tris, uint32_t ntris, const RptBVHNode* nodes, uint32_t nnodes,
+                       const float* rays_o_d, uint32_t nrays, uint64_t* out_stats) {
+    rpt::WideBvh wide;
+    const char* err = "";
+    if (!rpt::build_wide_bvh(nodes, nnodes, tris, ntris, verts, nverts, wide, &err)) return -1;
+    rpt::WideScene scene{reinterpret_cast<const rpt::uint4*>(wide.nodes.data()), reinterpret_cast<const rpt::float4*>(wide.tri_pos.data()), rpt::kHalf1024Bytes};
+    uint64_t visits = 0, empty = 0, tests = 0;
+    for (uint32_t i = 0; i < nrays; ++i) {
+        const float* r = rays_o_d + 6 * (size_t)i;
+        LocalStack st;
+        rpt::WideCursor<true> c;
+        c.begin(rpt::mk3(r[0], r[1], r[2]), rpt::mk3(r[3], r[4], r[5]), 0.0f);
+        while (c.has_nodes()) {
+            c.visit_node(scene, st);
+            ++visits;
+            if (!c.has_triangles() && c.last_child_hits == 0u) ++empty;
+            while (c.has_triangles()) { c.test_triangle(scene); ++tests; }
+        }
+    }
+    out_stats[0] = visits; out_stats[1] = empty; out_stats[2] = tests; out_stats[3] = nrays;
+    return 0;
+}
+
 // texel decoding of the shading kernels (dev/vec.cuh), for the exhaustive check against x / 255.0f
 float harness_unorm8(uint32_t x) { return rpt::unorm8(x); }
 
