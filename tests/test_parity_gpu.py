@@ -442,3 +442,52 @@ def test_more_materials_than_fit_in_shared_memory():
     want, *_ = render_cuda(base, cfg, seeds, 8, capi.PIPELINE_WAVEFRONT)
     got, *_ = render_cuda(many, cfg, seeds, 8, capi.PIPELINE_WAVEFRONT)
     np.testing.assert_array_equal(got, want)
+
+
+def _chain_world(ntris: int):
+    """A degenerate BVH: every inner node has one leaf child and one inner child (a chain as deep as the scene is large)."""
+    import dataclasses
+
+    from rust_path_tracer_b200.glb import MATERIAL_DTYPE, BakedScene
+    from rust_path_tracer_b200.world import World
+
+    v = np.zeros((3 * ntris, 4), np.float32)
+    for t in range(ntris):
+        v[3 * t:3 * t + 3, :3] = [[t, 0.0, 3.0], [t + 0.9, 0.0, 3.0], [t + 0.45, 1.0, 3.0]]
+    v[:, 3] = 1.0
+    n = np.tile(np.array([0, 0, -1, 0], np.float32), (3 * ntris, 1))
+    idx = np.zeros((ntris, 4), np.uint32)
+    idx[:, :3] = np.arange(3 * ntris, dtype=np.uint32).reshape(ntris, 3)
+    mats = np.zeros(1, MATERIAL_DTYPE)
+    mats[0]["albedo"] = (0.5, 0.5, 0.5, 1)
+    mats[0]["roughness"] = 1.0
+    world = World.from_baked(BakedScene(v, n, np.zeros((3 * ntris, 4), np.float32), np.zeros((3 * ntris, 2), np.float32), idx, mats))
+    # replace the SAH tree by the chain: node 2k = inner over triangles k.., node 2k+1 = leaf k, node 2k+2 = the rest
+    nodes = np.zeros(2 * ntris - 1, capi.BVH_NODE_DTYPE)
+    pos = v[:, :3].reshape(ntris, 3, 3)
+    tris = idx.copy()
+    k, at = 0, 0
+    while True:
+        rest = pos[k:].reshape(-1, 3)
+        nodes[at]["aabb_min"], nodes[at]["aabb_max"] = rest.min(0), rest.max(0)
+        if k == ntris - 1:
+            nodes[at]["triangle_count"], nodes[at]["left_or_first"] = 1, k
+            break
+        nodes[at]["triangle_count"], nodes[at]["left_or_first"] = 0, at + 1
+        leaf = at + 1
+        nodes[leaf]["aabb_min"], nodes[leaf]["aabb_max"] = pos[k].min(0), pos[k].max(0)
+        nodes[leaf]["triangle_count"], nodes[leaf]["left_or_first"] = 1, k
+        at, k = at + 2, k + 1
+    return dataclasses.replace(world, index_buffer=tris, nodes=nodes)
+
+
+def test_trees_deeper_than_the_traversal_stack_are_rejected_loudly():
+    """The wide tree's depth is checked at upload (kWideStackCapacity): no silent stack overflow on the device."""
+    with Renderer(0) as r:
+        r.upload_world(_chain_world(60))  # 8-wide collapse of a 60-deep chain: ~9 levels, fits
+        r.set_config(helpers.config(32, 32, 0)); r.write_rng(helpers.seeds(32, 32))
+        r.enqueue(1)
+        assert np.isfinite(r.read_output()).all()
+        with pytest.raises(capi.RptError) as e:
+            r.upload_world(_chain_world(400))
+        assert e.value.code == capi.ERR_UNSUPPORTED and "depth" in str(e.value)
