@@ -116,6 +116,7 @@ struct rpt_context {
     DevBuf<LightBin> d_light_bins;
     DevBuf<LightRecord> d_light_records;
     uint32_t nbins = 0;
+    bool deep_tree = false;  // the wide tree needs more stack entries than the shared slab holds
     bool has_world = false;
 
     // render state
@@ -135,7 +136,7 @@ struct rpt_context {
     // wave state
     uint32_t wave_capacity = 0;
     DevBuf<float4> w_ray_o, w_ray_d, w_thr, w_rad, w_sh_o, w_sh_d, w_sh_c;
-    DevBuf<uint2> w_hit;
+    DevBuf<uint2> w_hit, w_stack_overflow;
     DevBuf<uint32_t> w_q0, w_q1, w_qhit, w_qmiss, w_qshaded, w_qshadow;
     DevBuf<WaveCtl> w_ctl;
     DevBuf<unsigned long long> d_counters;
@@ -290,6 +291,8 @@ int ensure_wave(rpt_context* c, uint32_t slots) {
     RPT_CUDA(c, c->w_q0.alloc(slots)); RPT_CUDA(c, c->w_q1.alloc(slots)); RPT_CUDA(c, c->w_qhit.alloc(slots)); RPT_CUDA(c, c->w_qmiss.alloc(slots));
     RPT_CUDA(c, c->w_qshaded.alloc(slots)); RPT_CUDA(c, c->w_qshadow.alloc(slots));
     if (!c->w_ctl.p) RPT_CUDA(c, c->w_ctl.alloc(1));
+    // (only for trees deeper than the shared-memory part of the traversal stack)
+    if (c->deep_tree && !c->w_stack_overflow.p) RPT_CUDA(c, c->w_stack_overflow.alloc(trace_stack_overflow_entries(c->sm_count * c->trace_blocks_per_sm)));
     c->wave_capacity = slots;
     return RPT_OK;
 }
@@ -331,7 +334,7 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
     const FrameParams f = frame_params(c);
     const WideWorld w = wide_world(c);
     const WaveState s = wave_state(c);
-    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below};
+    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below, c->deep_tree ? c->w_stack_overflow.p : nullptr};
     const uint32_t nslots = d.npix * d.k_samples;
     c->launch(RPT_STAGE_OTHER, [&] { launch_wf_reset(l, s, 1, true); });
     c->launch(RPT_STAGE_GENERATE, [&] { launch_wf_generate(l, f, s, d, c->d_rng.p); });
@@ -465,7 +468,7 @@ extern "C" int rpt_destroy(rpt_context* c) {
     for (auto* b : {&c->w_ray_o, &c->w_ray_d, &c->w_thr, &c->w_rad, &c->w_sh_o, &c->w_sh_d, &c->w_sh_c, &c->d_tri_pos,
                     &c->d_tri_shade, &c->d_tri_tangent, &c->d_sky, &c->d_output})
         b->release();
-    c->w_hit.release(); c->w_q0.release(); c->w_q1.release(); c->w_qhit.release(); c->w_qmiss.release(); c->w_qshaded.release();
+    c->w_hit.release(); c->w_stack_overflow.release(); c->w_q0.release(); c->w_q1.release(); c->w_qhit.release(); c->w_qmiss.release(); c->w_qshaded.release();
     c->w_qshadow.release(); c->w_ctl.release();
     c->d_counters.release(); c->d_vertices.release(); c->d_triangles.release(); c->d_nodes.release(); c->d_materials.release();
     c->d_lights.release(); c->d_atlas.release(); c->d_wide_nodes.release(); c->d_light_bins.release(); c->d_light_records.release();
@@ -619,6 +622,9 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     RPT_CUDA(c, cudaStreamSynchronize(s));  // host staging vectors die at return
     c->nlights = nlights;
     c->nmaterials = nmaterials;
+    c->deep_tree = wide.max_depth + 1 > kWideStackShared;
+    if (c->deep_tree && c->wave_capacity != 0 && !c->w_stack_overflow.p)
+        RPT_CUDA(c, c->w_stack_overflow.alloc(trace_stack_overflow_entries(c->sm_count * c->trace_blocks_per_sm)));
     c->has_world = true;
     return RPT_OK;
 }

@@ -111,8 +111,10 @@ struct WaveLaunch {
     cudaStream_t stream;
     int trace_blocks_per_sm;  // resident 128-thread blocks per SM of the trace kernels
     int refill_below;         // refill idle lanes once fewer than this many lanes of a warp hold a ray
+    uint2* stack_overflow;    // global overflow area of the traversal stacks (trace_stack_overflow_entries); null when the tree fits the shared slab
 };
 
+size_t trace_stack_overflow_entries(int grid_blocks);  // uint2 entries the trace kernels need for a grid of that many blocks
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole);
 void launch_wf_generate(const WaveLaunch& l, const FrameParams& f, const WaveState& s, const WaveDesc& d, const uint2* rng);
 void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, int in_queue, bool identity_queue, uint32_t n_identity);

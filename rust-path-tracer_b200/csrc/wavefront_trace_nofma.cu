@@ -18,31 +18,31 @@ namespace rpt {
 
 constexpr int kTraceBlock = 128;  // 4 warps; 16 KB of stack slabs + the 2 KB permutation table per block
 constexpr int kTraceWarps = kTraceBlock / 32;
+size_t trace_stack_overflow_entries(int grid_blocks) { return (size_t)grid_blocks * kTraceBlock * (kWideStackCapacity - kWideStackShared); }
 
+// DEEP = false: the whole stack fits the shared slab (trees of at most kWideStackShared levels: every scene seen so
+// far); DEEP = true adds a global-memory overflow area for entries kWideStackShared.. so that deeper trees trace
+// correctly too (1 % slower, so the host only picks that variant when the tree needs it).
+template <bool DEEP>
 struct SmemStack {
-    uint2* column;  // this lane's column of the warp slab; entries are 32 lanes apart
+    uint2* column;    // this lane's column of the warp slab; entries are 32 lanes apart
     int n;
     const uint8_t* perm;  // the block's octant permutation table, [octant][child set]
+    uint2* overflow;  // this thread's column of the overflow area; entries are `overflow_stride` apart
+    uint32_t overflow_stride;
     __device__ __forceinline__ uint32_t permute(uint32_t oct, uint32_t m) const { return perm[oct * 256u + m]; }
-    __device__ __forceinline__ void push(uint2 v) {
-        if (n < (int)kWideStackCapacity) column[n * 32] = v;  // depth is validated at upload; never drop silently there
+    __device__ __forceinline__ void push(uint2 v) {  // (the tree's depth is validated at upload)
+        if (!DEEP || n < (int)kWideStackShared) column[n * 32] = v;
+        else overflow[(size_t)(n - (int)kWideStackShared) * overflow_stride] = v;
         ++n;
     }
-    __device__ __forceinline__ uint2 pop() { --n; return column[n * 32]; }
+    __device__ __forceinline__ uint2 pop() {
+        --n;
+        return (!DEEP || n < (int)kWideStackShared) ? column[n * 32] : overflow[(size_t)(n - (int)kWideStackShared) * overflow_stride];
+    }
     __device__ __forceinline__ bool empty() const { return n == 0; }
     __device__ __forceinline__ void clear() { n = 0; }
 };
-
-// Append `value` to a queue for every lane with `pred`; one atomic per warp.
-__device__ __forceinline__ void warp_append(bool pred, uint32_t* queue, uint32_t* count, uint32_t value) {
-    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
-    if (mask == 0u) return;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t base = 0;
-    if (lane == (uint32_t)(__ffs((int)mask) - 1)) base = atomicAdd(count, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)mask) - 1);
-    if (pred) queue[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = value;
-}
 
 __device__ __forceinline__ uint32_t wave_pixel(const WaveDesc& d, uint32_t j) {
     const uint32_t i = d.pix_base + j;
@@ -77,10 +77,10 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(FrameParams f, WaveSta
 
 constexpr uint32_t kMissRecord = 0xFFFFFFFFu;  // hit[].y of a ray that hit nothing (triangle indices are < 2^31)
 
-template <bool NEAREST>
+template <bool NEAREST, bool DEEP>
 __global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
-                                                               int refill_below) {
-    __shared__ uint2 slabs[kTraceWarps][kWideStackCapacity][32];
+                                                               int refill_below, uint2* stack_overflow) {
+    __shared__ uint2 slabs[kTraceWarps][kWideStackShared][32];
     __shared__ uint8_t perm_table[8 * 256];
     for (uint32_t i = threadIdx.x; i < 8u * 256u; i += kTraceBlock) perm_table[i] = (uint8_t)octant_permute(i >> 8, i & 0xFFu);
     __syncthreads();
@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh,
     uint32_t* fetch = NEAREST ? &s.ctl->fetch_extend : &s.ctl->fetch_shadow;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.counters + (NEAREST ? 1 : 2), (unsigned long long)n);
 
-    SmemStack st{&slabs[warp][0][lane], 0, perm_table};
+    SmemStack<DEEP> st{&slabs[warp][0][lane], 0, perm_table, DEEP ? stack_overflow + (size_t)blockIdx.x * kTraceBlock + threadIdx.x : nullptr,
+                       gridDim.x * kTraceBlock};
     WideCursor<NEAREST> c;
     uint32_t item = 0;       // path slot (NEAREST) / index of the shadow ray (ANY)
     bool busy = false;       // this lane holds an unfinished ray
@@ -277,14 +278,20 @@ void launch_wf_generate(const WaveLaunch& l, const FrameParams& f, const WaveSta
     wf_generate_kernel<<<l.grid * 8, 256, 0, l.stream>>>(f, s, d, rng);
 }
 void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, int in_queue, bool identity_queue, uint32_t n_identity) {
-    wf_trace_kernel<true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below);
+    if (l.stack_overflow)
+        wf_trace_kernel<true, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.stack_overflow);
+    else
+        wf_trace_kernel<true, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, nullptr);
     wf_compact_kernel<<<l.grid * 8, kCompactBlock, 0, l.stream>>>(s, in_queue, identity_queue, n_identity);
 }
 void launch_wf_compact_shaded(const WaveLaunch& l, const WaveState& s, int out_queue) {
     wf_compact_shaded_kernel<<<l.grid * 8, kCompactBlock, 0, l.stream>>>(s, out_queue);
 }
 void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState& s) {
-    wf_trace_kernel<false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below);
+    if (l.stack_overflow)
+        wf_trace_kernel<false, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.stack_overflow);
+    else
+        wf_trace_kernel<false, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, nullptr);
 }
 void launch_wf_export_primary(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, const WaveDesc& d, uint32_t* ids) {
     wf_export_primary_kernel<<<(d.npix + 255) / 256, 256, 0, l.stream>>>(bvh, s, d, ids);

@@ -48,6 +48,10 @@ struct WideBvh {
 bool build_wide_bvh(const RptBVHNode* nodes, uint32_t nnodes, const uint32_t* triangles, uint32_t ntriangles,
                     const RptPerVertexData* vertices, uint32_t nvertices, WideBvh& out, const char** error);
 
-constexpr uint32_t kWideStackCapacity = 16;  // 8-wide: a 1M-triangle scene is 10 levels deep; deeper trees are rejected at upload
+// Traversal stack: the first kWideStackShared entries of a lane live in shared memory (8-wide: a 1M-triangle scene
+// is 10 levels deep), deeper ones in a global-memory overflow area; trees deeper than kWideStackCapacity are
+// rejected at upload.
+constexpr uint32_t kWideStackShared = 16;
+constexpr uint32_t kWideStackCapacity = 64;
 
 }  // namespace rpt

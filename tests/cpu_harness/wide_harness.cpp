@@ -17,7 +17,7 @@ struct LocalStack {
     rpt::uint2 data[rpt::kWideStackCapacity];
     int n = 0;
     int high_water = 0;
-    void push(rpt::uint2 v) { data[n++] = v; if (n > high_water) high_water = n; }
+    void push(rpt::uint2 v) { if (n < (int)rpt::kWideStackCapacity) data[n] = v; ++n; if (n > high_water) high_water = n; }  // (callers check high_water)
     rpt::uint2 pop() { return data[--n]; }
     bool empty() const { return n == 0; }
     void clear() { n = 0; }

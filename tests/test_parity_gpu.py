@@ -444,50 +444,132 @@ def test_more_materials_than_fit_in_shared_memory():
     np.testing.assert_array_equal(got, want)
 
 
-def _chain_world(ntris: int):
-    """A degenerate BVH: every inner node has one leaf child and one inner child (a chain as deep as the scene is large)."""
-    import dataclasses
-
-    from rust_path_tracer_b200.glb import MATERIAL_DTYPE, BakedScene
+def _deep_world(nclusters: int):
+    """A BVH whose 8-wide collapse is about nclusters / 7 levels deep AND makes rays push at every level: a chain
+    node_k = {cluster_k, node_k+1} of 16-triangle clusters in the planes x = k, far clusters larger than near ones;
+    a ray travelling towards -x descends the chain first (its nearer child), stacking the clusters of every level."""
+    from rust_path_tracer_b200.glb import MATERIAL_DTYPE, VERTEX_DTYPE
     from rust_path_tracer_b200.world import World
 
-    v = np.zeros((3 * ntris, 4), np.float32)
-    for t in range(ntris):
-        v[3 * t:3 * t + 3, :3] = [[t, 0.0, 3.0], [t + 0.9, 0.0, 3.0], [t + 0.45, 1.0, 3.0]]
-    v[:, 3] = 1.0
-    n = np.tile(np.array([0, 0, -1, 0], np.float32), (3 * ntris, 1))
-    idx = np.zeros((ntris, 4), np.uint32)
-    idx[:, :3] = np.arange(3 * ntris, dtype=np.uint32).reshape(ntris, 3)
+    verts, tris = [], []
+    for k in range(nclusters):
+        half = 1.0 + 1.0 * (nclusters - 1 - k)  # grows faster than the distance: every cluster shows a rim around the nearer ones
+        ys, zs = np.linspace(1.0 - half, 1.0 + half, 3), np.linspace(-half, half, 5)
+        for iy in range(2):
+            for iz in range(4):
+                quad = [(k, ys[iy], zs[iz]), (k, ys[iy + 1], zs[iz]), (k, ys[iy + 1], zs[iz + 1]), (k, ys[iy], zs[iz + 1])]
+                base = len(verts)
+                verts += quad
+                tris += [(base, base + 1, base + 2, 0), (base, base + 2, base + 3, 0)]
+    pos = np.asarray(verts, np.float32)
+    tris = np.asarray(tris, np.uint32)
+    packed = np.zeros(len(pos), VERTEX_DTYPE)
+    packed["vertex"][:, :3] = pos
+    packed["vertex"][:, 3] = 1.0
+    packed["normal"][:, 0] = 1.0
+    tri_lo, tri_hi = pos[tris[:, :3]].min(axis=1), pos[tris[:, :3]].max(axis=1)
+    nodes = []
+
+    def box(first, count):
+        return tri_lo[first:first + count].min(axis=0), tri_hi[first:first + count].max(axis=0)
+
+    def emit(first, count):  # children of a node are adjacent, like the reference builder's
+        me = len(nodes)
+        nodes.append(None)
+        return me
+
+    def fill_leafy(at, first, count):  # balanced subtree over one cluster
+        lo, hi = box(first, count)
+        if count == 1:
+            nodes[at] = (lo, 1, hi, first)
+            return
+        left = len(nodes)
+        nodes.extend([None, None])
+        nodes[at] = (lo, 0, hi, left)
+        fill_leafy(left, first, count // 2)
+        fill_leafy(left + 1, first + count // 2, count - count // 2)
+
+    nodes.append(None)
+    at = 0
+    for k in range(nclusters):
+        first = 16 * k
+        if k == nclusters - 1:
+            fill_leafy(at, first, 16)
+            break
+        lo, hi = box(first, 16 * (nclusters - k))
+        left = len(nodes)
+        nodes.extend([None, None])
+        nodes[at] = (lo, 0, hi, left)
+        fill_leafy(left, first, 16)
+        at = left + 1
+    arr = np.zeros(len(nodes), capi.BVH_NODE_DTYPE)
+    for i, (lo, cnt, hi, ref) in enumerate(nodes):
+        arr[i] = (lo, cnt, hi, ref)
     mats = np.zeros(1, MATERIAL_DTYPE)
     mats[0]["albedo"] = (0.5, 0.5, 0.5, 1)
     mats[0]["roughness"] = 1.0
-    world = World.from_baked(BakedScene(v, n, np.zeros((3 * ntris, 4), np.float32), np.zeros((3 * ntris, 2), np.float32), idx, mats))
-    # replace the SAH tree by the chain: node 2k = inner over triangles k.., node 2k+1 = leaf k, node 2k+2 = the rest
-    nodes = np.zeros(2 * ntris - 1, capi.BVH_NODE_DTYPE)
-    pos = v[:, :3].reshape(ntris, 3, 3)
-    tris = idx.copy()
-    k, at = 0, 0
-    while True:
-        rest = pos[k:].reshape(-1, 3)
-        nodes[at]["aabb_min"], nodes[at]["aabb_max"] = rest.min(0), rest.max(0)
-        if k == ntris - 1:
-            nodes[at]["triangle_count"], nodes[at]["left_or_first"] = 1, k
-            break
-        nodes[at]["triangle_count"], nodes[at]["left_or_first"] = 0, at + 1
-        leaf = at + 1
-        nodes[leaf]["aabb_min"], nodes[leaf]["aabb_max"] = pos[k].min(0), pos[k].max(0)
-        nodes[leaf]["triangle_count"], nodes[leaf]["left_or_first"] = 1, k
-        at, k = at + 2, k + 1
-    return dataclasses.replace(world, index_buffer=tris, nodes=nodes)
+    lights = np.zeros(1, capi.LIGHT_DTYPE)
+    lights[0]["ratio"] = -1.0  # the "no lights" sentinel
+    return World(packed, tris, arr, mats, lights)
 
 
-def test_trees_deeper_than_the_traversal_stack_are_rejected_loudly():
-    """The wide tree's depth is checked at upload (kWideStackCapacity): no silent stack overflow on the device."""
+def _brute_force_primary_ids(world, cfg, seeds):
+    """Nearest triangle per pixel by testing every triangle (float64), for sample index 0 of the given seeds."""
+    from rust_path_tracer_b200.capi import TracingConfig  # noqa: F401
+
+    primes = (0xbb67ae84, 0x3c6ef372)  # LDS_PRIMES[1], [2]: the two jitter dimensions (kernels/src/rng.rs:19-27, 51-58)
+    w, h = cfg.width, cfg.height
+    key = (seeds[:, 0].astype(np.uint64) + seeds[:, 1].astype(np.uint64)) & 0xFFFFFFFF
+    jx = ((key * primes[0]) & 0xFFFFFFFF).astype(np.float64) / 2.0 ** 32
+    jy = ((key * primes[1]) & 0xFFFFFFFF).astype(np.float64) / 2.0 ** 32
+    px, py = np.meshgrid(np.arange(w), np.arange(h))
+    ux = ((px.ravel() + jx) / w) * 2 - 1
+    uy = ((1 - (py.ravel() + jy) / h) * 2 - 1) * (h / w)
+    d = np.stack([ux, uy, np.ones_like(ux)], axis=1)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rx, ry = float(cfg.cam_rotation[0]), float(cfg.cam_rotation[1])
+    rot_x = np.array([[1, 0, 0], [0, np.cos(rx), -np.sin(rx)], [0, np.sin(rx), np.cos(rx)]])
+    rot_y = np.array([[np.cos(ry), 0, np.sin(ry)], [0, 1, 0], [-np.sin(ry), 0, np.cos(ry)]])
+    d = d @ (rot_y @ rot_x).T
+    o = np.array(cfg.cam_position[:3], np.float64)
+    pos = world.per_vertex_buffer["vertex"][:, :3].astype(np.float64)
+    tri = world.index_buffer[:, :3]
+    a, e1, e2 = pos[tri[:, 0]], pos[tri[:, 1]] - pos[tri[:, 0]], pos[tri[:, 2]] - pos[tri[:, 0]]
+    best_t = np.full(len(d), 1e6)
+    best = np.full(len(d), 0xFFFFFFFF, np.uint32)
+    for i in range(len(tri)):
+        pv = np.cross(d, e2[i])
+        det = pv @ e1[i]
+        ok = np.abs(det) >= 1e-6
+        inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+        tv = o - a[i]
+        u = (pv @ tv) * inv
+        qv = np.cross(tv, e1[i])
+        v = (d @ qv) * inv
+        t = (qv @ e2[i]) * inv
+        hit = ok & (u >= 0) & (u <= 1) & (v >= 0) & (u + v <= 1) & (t > 0.001) & (t < best_t)
+        best_t[hit] = t[hit]
+        best[hit] = i
+    return best
+
+
+def test_deep_trees_overflow_to_global_memory_and_deeper_ones_are_rejected_loudly():
+    """The first 16 stack entries of a lane live in shared memory, the next 48 in a global overflow area; the wide
+    tree's depth is checked at upload (kWideStackCapacity = 64): no silent stack overflow on the device.  (The
+    reference's own 32-entry stack overflows on such a scene, so the checker here is a brute-force nearest hit.)"""
+    seeds = helpers.seeds(64, 32)
+    for nclusters in (40, 200):  # wide depth 10 (shared memory only) and 50 (overflow area)
+        world = _deep_world(nclusters)
+        cfg = helpers.config(64, 32, 0, cam_position=[nclusters + 0.2, 1.0, 0.0, 0.0], cam_rotation=[0.0, -float(np.pi) / 2, 0.0, 0.0])
+        want = _brute_force_primary_ids(world, cfg, seeds)
+        with Renderer(0) as r:
+            r.upload_world(world); r.set_config(cfg); r.write_rng(seeds)
+            got = r.read_primary_ids()
+            r.enqueue(2)
+            assert np.isfinite(r.read_output()).all()
+        assert (want != 0xFFFFFFFF).mean() > 0.3, "the camera must look at the clusters"
+        assert (got != want).mean() <= 2e-3, (nclusters, float((got != want).mean()))
     with Renderer(0) as r:
-        r.upload_world(_chain_world(60))  # 8-wide collapse of a 60-deep chain: ~9 levels, fits
-        r.set_config(helpers.config(32, 32, 0)); r.write_rng(helpers.seeds(32, 32))
-        r.enqueue(1)
-        assert np.isfinite(r.read_output()).all()
         with pytest.raises(capi.RptError) as e:
-            r.upload_world(_chain_world(400))
+            r.upload_world(_deep_world(330))  # wide depth 83
         assert e.value.code == capi.ERR_UNSUPPORTED and "depth" in str(e.value)
