@@ -148,13 +148,17 @@ struct rpt_context {
     // scene, the config, the buffers and the wave's shape, so it is captured once and replayed: one launch per
     // wave instead of thirty, which is what bounds small frames (a 128x128 x 32 spp batch is ~150 us of GPU work).
     // `graph_epoch` moves whenever something baked into the captured arguments changes.
+    // A shape is captured the second time it runs in an epoch: a host that changes the config before every batch
+    // (camera motion: `interacting` flushes after each sample, src/trace.rs:187-193) never pays for a capture.
     struct WaveGraph { WaveDesc desc; uint64_t epoch; cudaGraphExec_t exec; uint64_t launches; };
     std::vector<WaveGraph> wave_graphs;
+    std::vector<WaveDesc> shapes_run_once;
     uint64_t graph_epoch = 0;
     bool use_graphs = true;  // RPT_GRAPHS=0 turns them off
     void drop_graphs() {
         for (auto& g : wave_graphs) cudaGraphExecDestroy(g.exec);
         wave_graphs.clear();
+        shapes_run_once.clear();
         ++graph_epoch;
     }
     bool stage_timing = false;
@@ -374,6 +378,12 @@ int run_wave_graphed(rpt_context* c, const WaveDesc& d) {
             c->kernel_launches += g.launches;
             return c->cuda(cudaGraphLaunch(g.exec, c->stream), "cudaGraphLaunch");
         }
+    auto same = [&](const WaveDesc& o) { return o.pix_base == d.pix_base && o.npix == d.npix && o.k_samples == d.k_samples && o.pixel_map == d.pixel_map; };
+    if (std::none_of(c->shapes_run_once.begin(), c->shapes_run_once.end(), same)) {
+        if (c->shapes_run_once.size() >= 64) c->shapes_run_once.clear();
+        c->shapes_run_once.push_back(d);
+        return run_wave(c, d, false, nullptr);
+    }
     if (c->wave_graphs.size() >= 16) c->drop_graphs();  // (a frame is a handful of wave shapes)
     const uint64_t before = c->kernel_launches;
     RPT_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
