@@ -6,6 +6,8 @@
 // triangle and the same t bits as the reference traversal restated in oracle/oracle.cpp.
 // It is not part of the product: nothing under rust-path-tracer_b200/ builds or loads it.
 #include <cstdint>
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -49,6 +51,79 @@ int harness_wide_stats(const RptPerVertexData* verts, uint32_t nverts, const uin
         }
     }
     out_stats[0] = visits; out_stats[1] = empty; out_stats[2] = tests; out_stats[3] = nrays;
+    return 0;
+}
+
+// Experiment: the same wide tree traversed with EXACT front-to-back order and per-entry distance culling (every hit
+// inner child is pushed with its entry distance, far ones first; a popped entry whose distance is not below the best
+// hit is dropped without a visit).  Statistics as harness_wide_stats: [0] node visits, [1] entries culled at pop,
+// [2] triangle tests, [3] rays, [4] stack high-water.
+int harness_wide_stats_sorted(const RptPerVertexData* verts, uint32_t nverts, const uint32_t* tris, uint32_t ntris, const RptBVHNode* nodes,
+                              uint32_t nnodes, const float* rays_o_d, uint32_t nrays, uint64_t* out_stats) {
+    rpt::WideBvh wide;
+    const char* err = "";
+    if (!rpt::build_wide_bvh(nodes, nnodes, tris, ntris, verts, nverts, wide, &err)) return -1;
+    uint64_t visits = 0, culled = 0, tests = 0, high = 0;
+    struct Entry { uint32_t node; float tn; };
+    std::vector<Entry> stack;
+    for (uint32_t i = 0; i < nrays; ++i) {
+        const float* r = rays_o_d + 6 * (size_t)i;
+        const rpt::f3 ro = rpt::mk3(r[0], r[1], r[2]), rd = rpt::mk3(r[3], r[4], r[5]);
+        const float idir[3] = {rpt::safe_rcp(rd.x), rpt::safe_rcp(rd.y), rpt::safe_rcp(rd.z)};
+        const float o[3] = {ro.x, ro.y, ro.z};
+        float best = 1000000.0f;
+        stack.clear();
+        stack.push_back({0u, 0.0f});
+        while (!stack.empty()) {
+            const Entry e = stack.back();
+            stack.pop_back();
+            if (e.tn >= best) { ++culled; continue; }
+            ++visits;
+            const uint32_t* w = wide.nodes[e.node].w;
+            float p[3], cell[3];
+            std::memcpy(p, w, 12);
+            const uint32_t cb[3] = {w[3], w[7] << 16, w[7] & 0xFFFF0000u};
+            std::memcpy(cell, cb, 12);
+            const uint32_t imask = w[6] >> 24, valid = w[6] & 0x00FFFFFFu;
+            Entry kids[8];
+            int nk = 0;
+            uint32_t below_inner = 0, tri_rank = 0;
+            for (uint32_t s = 0; s < 8; ++s) {
+                const bool inner = (imask >> s) & 1u;
+                const uint32_t tbits = (valid >> (3 * s)) & 7u;
+                float tn = 0.0f, tf = best;
+                // plane bytes: qlo_x w[8..9], qlo_y w[10..11], qlo_z w[12..13], qhi_x w[14..15], qhi_y w[16..17], qhi_z w[18..19]
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t qlo = (w[8 + 2 * k + s / 4] >> (8 * (s % 4))) & 0xFFu, qhi = (w[14 + 2 * k + s / 4] >> (8 * (s % 4))) & 0xFFu;
+                    const float t0 = ((p[k] + (float)qlo * cell[k]) - o[k]) * idir[k], t1 = ((p[k] + (float)qhi * cell[k]) - o[k]) * idir[k];
+                    tn = std::fmax(tn, std::fmin(t0, t1));
+                    tf = std::fmin(tf, std::fmax(t0, t1));
+                }
+                const bool hit = (inner || tbits) && tn <= tf;
+                if (inner) {
+                    if (hit) kids[nk++] = {w[4] + below_inner, tn};
+                    ++below_inner;
+                } else {
+                    const uint32_t cnt = tbits == 7u ? 3u : (tbits == 3u ? 2u : (tbits == 1u ? 1u : 0u));
+                    if (hit)
+                        for (uint32_t t = 0; t < cnt; ++t) {
+                            const float* rec = wide.tri_pos.data() + 12 * (size_t)(w[5] + tri_rank + t);
+                            float tt;
+                            bool back;
+                            ++tests;
+                            if (rpt::ray_triangle(ro, rd, rpt::mk3(rec[0], rec[1], rec[2]), rpt::mk3(rec[4], rec[5], rec[6]), rpt::mk3(rec[8], rec[9], rec[10]), tt, back) &&
+                                tt > 0.001f && tt < best)
+                                best = tt;
+                        }
+                    tri_rank += cnt;
+                }
+            }
+            std::sort(kids, kids + nk, [](const Entry& a, const Entry& b) { return a.tn > b.tn; });  // far first: the nearest is popped next
+            for (int k = 0; k < nk; ++k) stack.push_back(kids[k]);
+            if (stack.size() > high) high = stack.size();
+        }
+    }
+    out_stats[0] = visits; out_stats[1] = culled; out_stats[2] = tests; out_stats[3] = nrays; out_stats[4] = high;
     return 0;
 }
 
