@@ -72,7 +72,19 @@ struct WideRay {
     uint32_t oct_inv;  // dx>=0 ? 4 : 0 | dy>=0 ? 2 : 0 | dz>=0 ? 1 : 0
 };
 
-RPT_D float safe_rcp(float d) { return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
+// 1 / d with |d| clamped away from 0.  It only feeds the conservative box tests, so the device uses the 1-ulp
+// MUFU reciprocal instead of the IEEE division (three divisions per ray at refill time, where few lanes are
+// enabled); the extra half ulp is part of the padding budget below.
+RPT_D float safe_rcp(float d) {
+    const float clamped = fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d);
+#if defined(__CUDACC__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(clamped));
+    return r;
+#else
+    return 1.0f / clamped;
+#endif
+}
 
 RPT_D WideRay make_wide_ray(f3 o, f3 d) {
     WideRay r;
@@ -206,13 +218,13 @@ struct WideCursor {
         const f3 cell = mk3(as_float(n0.w), as_float(n1.w << 16), as_float(n1.w & 0xFFFF0000u));  // powers of two
         const f3 adj = cell * ray.idir;
         // Push the planes out so rounding can never cull a box the exact arithmetic would enter.  p - o, its
-        // product with idir and the final FMA are each correctly rounded, i.e. off by < 2^-23 of |p - o| resp.
-        // of the box extent (<= 256 cells): pad by 2^-21 (4.8e-7) of both.  Folding the -1024 bias of the fp16
+        // product with idir and the final FMA are each correctly rounded and idir is within 1 ulp of 1/d, i.e.
+        // together off by < 3 * 2^-23 of |p - o| resp. of the box extent (<= 256 cells): pad by 5 * 2^-23 (6e-7) of both.  Folding the -1024 bias of the fp16
         // de-quantisation into the addend rounds it at magnitude 1024 |adj|, i.e. by < 2^-14 |adj|: 512 more
         // cells in the same pad term cover that four times over.
         const f3 rel_o = p - ray.o;
-        const f3 apad = mk3(fabsf(fmaf(768.0f, cell.x, fabsf(rel_o.x)) * ray.idir.x) * 4.8e-7f, fabsf(fmaf(768.0f, cell.y, fabsf(rel_o.y)) * ray.idir.y) * 4.8e-7f,
-                            fabsf(fmaf(768.0f, cell.z, fabsf(rel_o.z)) * ray.idir.z) * 4.8e-7f);
+        const f3 apad = mk3(fabsf(fmaf(768.0f, cell.x, fabsf(rel_o.x)) * ray.idir.x) * 6e-7f, fabsf(fmaf(768.0f, cell.y, fabsf(rel_o.y)) * ray.idir.y) * 6e-7f,
+                            fabsf(fmaf(768.0f, cell.z, fabsf(rel_o.z)) * ray.idir.z) * 6e-7f);
         const f3 org = rel_o * ray.idir;
         const f3 org_near = mk3(fmaf(adj.x, -1024.0f, org.x - apad.x), fmaf(adj.y, -1024.0f, org.y - apad.y), fmaf(adj.z, -1024.0f, org.z - apad.z));
         const f3 org_far = mk3(fmaf(adj.x, -1024.0f, org.x + apad.x), fmaf(adj.y, -1024.0f, org.y + apad.y), fmaf(adj.z, -1024.0f, org.z + apad.z));
