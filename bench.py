@@ -141,9 +141,23 @@ def load_workload(name):
     elif name in ("breaktime", "breaktime-4k"):
         from rust_path_tracer_b200.scenes import breaktime_proxy, synthetic_hdr_sky
 
-        baked, atlas = breaktime_proxy()
-        world = World.from_baked(baked, atlas=atlas)
-        sky = synthetic_hdr_sky()
+        # The real asset is used when someone supplies it (it is absent from the reference checkout): scenes/BreakTime.glb
+        # in this repo, or RPT_BREAKTIME_GLB=<path>; RPT_BREAKTIME_SKY=<.npy float lat-long image> likewise.
+        real = os.environ.get("RPT_BREAKTIME_GLB") or os.path.join(REPO, "scenes", "BreakTime.glb")
+        world = World.from_path(real) if os.path.exists(real) else None
+        if world is not None:
+            label = label.replace(" — asset absent, LABELLED SYNTHETIC PROXY", "").replace(" (use --partition tiles)", "")
+            scene = "BreakTime.glb (the real asset, supplied at run time)"
+        else:
+            baked, atlas = breaktime_proxy()
+            world = World.from_baked(baked, atlas=atlas)
+        sky_path = os.environ.get("RPT_BREAKTIME_SKY")
+        if sky_path and os.path.exists(sky_path):
+            from rust_path_tracer_b200.trace import load_skybox
+
+            sky = load_skybox(sky_path)
+        if sky is None:
+            sky = synthetic_hdr_sky()
         cfg.has_skybox = 1
     else:
         world = World.from_path(os.path.join(REPO, "tests", "golden", "scenes", scene + ".npz"))
