@@ -573,3 +573,24 @@ def test_deep_trees_overflow_to_global_memory_and_deeper_ones_are_rejected_loudl
         with pytest.raises(capi.RptError) as e:
             r.upload_world(_deep_world(330))  # wide depth 83
         assert e.value.code == capi.ERR_UNSUPPORTED and "depth" in str(e.value)
+
+
+@pytest.mark.parametrize("nee", [0, 1], ids=["nee_off", "mis"])
+def test_config0_furnace_at_its_full_size(nee):
+    """configs[0] as BASELINE.json states it: FurnaceTest 256x256, 64 spp — every sample of the frame against the
+    oracle, and the furnace's energy balance on the image itself (tests/correctness_tests.rs:15-32: the grey sphere
+    inside the emissive shell reads 0.8 after the 1/2.2 gamma)."""
+    world = helpers.world("FurnaceTest")
+    w = h = 256
+    cfg = helpers.config(w, h, nee)
+    seeds = helpers.seeds(w, h)
+    o_out, o_rng, o_ids, _ = render_oracle(world, cfg, seeds, 64)
+    c_out, c_rng, c_ids, ctr = render_cuda(world, cfg, seeds, 64, capi.PIPELINE_WAVEFRONT)
+    np.testing.assert_array_equal(c_rng, o_rng)
+    mismatch = float((c_ids != o_ids).mean())
+    err, bad = helpers.mae(c_out[:, :3] / 64, o_out[:, :3] / 64)
+    helpers.record_parity(f"FurnaceTest 256x256 64spp nee={nee} (configs[0])", id_mismatch=mismatch, mae=err, nan_pixels=bad)
+    assert mismatch <= ID_MISMATCH_BUDGET and err <= MAE_TOLERANCE and ctr["paths"] == w * h * 64
+    # the reference's test pixel (65, 75) of its 128^2 frame is (130, 150) here: the grey sphere, seen from (0, 1, -5)
+    sphere = (c_out[:, :3] / 64).reshape(h, w, 3)[142:158, 122:138].mean(axis=(0, 1))
+    assert np.all(np.abs(sphere ** (1 / 2.2) - 0.8) < 0.02), sphere
