@@ -15,7 +15,9 @@ for setting in sys.argv[3:] or [""]:
         os.environ[k] = v
     with Renderer(0) as r:
         r.upload_world(world, sky); r.set_config(cfg); r.write_rng(seeds)
-        r.enqueue(spp); r.sync()
+        for _ in range(3):  # direct run, graph capture, first replay
+            r.enqueue(spp)
+        r.sync()
         r.reset_counters(); r.enqueue(spp); ms = r.device_ms(); c = r.counters()
         r.set_stage_timing(True); r.enqueue(spp); st = r.stage_timing()
     rays = c["nearest_rays"] + c["any_rays"]
