@@ -594,3 +594,24 @@ def test_config0_furnace_at_its_full_size(nee):
     # the reference's test pixel (65, 75) of its 128^2 frame is (130, 150) here: the grey sphere, seen from (0, 1, -5)
     sphere = (c_out[:, :3] / 64).reshape(h, w, 3)[142:158, 122:138].mean(axis=(0, 1))
     assert np.all(np.abs(sphere ** (1 / 2.2) - 0.8) < 0.02), sphere
+
+
+def test_primary_ids_at_later_sample_indices():
+    """ID parity is stated for sample indices 0..k: the jitter changes with the index, the ids must
+    follow the oracle's at every one of them."""
+    world = helpers.world("PBRTest")
+    cfg = helpers.config(160, 88, 0)
+    seeds = helpers.seeds(160, 88)
+    scene = oracle_mod.OracleScene(world)
+    with Renderer(0) as r:
+        r.upload_world(world); r.set_config(cfg); r.write_rng(seeds)
+        for index in (0, 1, 2, 7):
+            while int(r.read_rng()[0, 0]) < index:
+                r.enqueue(1)
+            state = r.read_rng()
+            assert (state[:, 0] == index).all()
+            _, _, _, want = oracle_mod.trace(cfg, scene, state, 1, want_primary_ids=True)
+            got = r.read_primary_ids()
+            mismatch = float((got != want).mean())
+            helpers.record_parity(f"PBRTest 160x88 primary ids at sample index {index}", id_mismatch=mismatch)
+            assert mismatch <= ID_MISMATCH_BUDGET, (index, mismatch)
