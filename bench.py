@@ -350,6 +350,8 @@ def run_b200(args):
         if tr:  # dram__bytes_read.sum + dram__bytes_write.sum of the profiled launch, scaled to this launch's ray count
             line["roofline"]["traffic"] = tr["dram_bytes_per_ray"] * line["roofline"]["rays_per_launch"]
             line["roofline"]["traffic_source"] = tr["source"]
+            # what actually bounds the kernel (the scene is on chip): issue slots at the SIMT efficiency of incoherent rays
+            line["roofline"]["issue"] = {k: tr[k] for k in ("issue_active_pct_of_peak", "lanes_per_instruction", "warp_instructions_per_ray") if k in tr}
     if rank == 0 and not args.quick and dist is None:
         # ---- CPU baseline (N = 1 only): the oracle port on the host cores, bounded sample -----
         cpu_spp = max(1, min(8, int(15.0 / max(dt1, 1e-3))))

@@ -23,13 +23,16 @@ def main():
 
     def metric(name):
         c = head.index(name)
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[c]]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[c], 1.0)
         return float(row[c]) * scale
 
     total = metric("dram__bytes_read.sum") + metric("dram__bytes_write.sum")
     path = os.path.join(REPO, "profiles", "extend_traffic.json")
     table = json.load(open(path)) if os.path.exists(path) else {}
     table[workload] = {"dram_bytes_per_ray": total / rays, "dram_bytes_in_profiled_launch": total, "rays_in_profiled_launch": rays,
+                       "issue_active_pct_of_peak": metric("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                       "lanes_per_instruction": metric("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                       "warp_instructions_per_ray": metric("smsp__inst_executed.sum") / rays,
                        "source": os.path.basename(rep) + f" (ncu --set full, wf_trace_kernel<true> launch {index})"}
     json.dump(table, open(path, "w"), indent=1, sort_keys=True)
     print(workload, table[workload])
