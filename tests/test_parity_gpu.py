@@ -615,3 +615,27 @@ def test_primary_ids_at_later_sample_indices():
             mismatch = float((got != want).mean())
             helpers.record_parity(f"PBRTest 160x88 primary ids at sample index {index}", id_mismatch=mismatch)
             assert mismatch <= ID_MISMATCH_BUDGET, (index, mismatch)
+
+
+def test_create_destroy_cycles_do_not_leak():
+    """criterion calls trace_gpu a dozen times per bench (benches/benchmark.rs): contexts must give everything back."""
+    import torch
+
+    world = helpers.world("DarkCornell")
+    cfg = helpers.config(256, 256, 1)
+    seeds = helpers.seeds(256, 256)
+
+    def cycle():
+        with Renderer(0) as r:
+            r.upload_world(world); r.set_config(cfg); r.write_rng(seeds)
+            r.enqueue(2); r.enqueue(2)
+            return r.read_output()
+
+    first = cycle()
+    torch.cuda.synchronize()
+    free_before, _ = torch.cuda.mem_get_info(0)
+    for _ in range(12):
+        np.testing.assert_array_equal(cycle(), first)
+    torch.cuda.synchronize()
+    free_after, _ = torch.cuda.mem_get_info(0)
+    assert free_before - free_after < 64 << 20, (free_before, free_after)  # (allocator caches aside, nothing accumulates)
