@@ -104,6 +104,16 @@ int rpt_sync(rpt_context* ctx);                        /* FW.poll_blocking() */
 int rpt_read_output(rpt_context* ctx, float* rgba, size_t npixels);
 /* Packed RGB `output.xyz / samples` normalised on the device (src/trace.rs:199-204). */
 int rpt_read_framebuffer(rpt_context* ctx, float* rgb, size_t npixels, float samples);
+/* Display resolve on the device — the fragment stage of src/resources/render.wgsl:150-185 (fs_main):
+ * rgb = tonemap(output.xyz / samples), row-major, top-left origin.  `tonemap` is the reference's `Tonemapping`
+ * enum value (src/app.rs:20-28): 0 none, 1 Reinhard, 2 ACES Narkowicz (input x 0.6), 3 ACES Narkowicz
+ * "overexposed", 4 ACES Hill, 5 Neutral, 6 Uncharted; any other value means none, like the shader's default arm. */
+int rpt_read_display(rpt_context* ctx, float* rgb, size_t npixels, float samples, uint32_t tonemap);
+/* The same, stored as the colour attachment save_render reads back (src/app.rs:759-840): 4 bytes per pixel in
+ * R,G,B,A order (the reference swizzles its BGRA surface to this before writing the PNG), alpha 255, channels
+ * clamped to [0,1] (NaN -> 0) and rounded to the nearest of 256 levels; srgb_encode != 0 applies the linear ->
+ * sRGB transfer first, which is what an *Srgb surface format does in hardware.  A third of the readback bytes. */
+int rpt_read_display_rgba8(rpt_context* ctx, uint8_t* rgba, size_t npixels, float samples, uint32_t tonemap, uint32_t srgb_encode);
 /* Diagnostics: bounce-0 triangle_index per pixel (0xFFFFFFFF = miss) for the NEXT sample index
  * of the current rng state, without advancing any state. */
 int rpt_read_primary_ids(rpt_context* ctx, uint32_t* triangle_ids, size_t npixels);

@@ -18,6 +18,8 @@ OK = 0
 ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_NOT_READY = -1, -2, -3, -4
 ERR_RNG_DIMENSIONS, ERR_SIZE_MISMATCH, ERR_NCCL, ERR_UNSUPPORTED = -5, -6, -7, -8
 PIPELINE_WAVEFRONT, PIPELINE_MEGAKERNEL = 0, 1
+# `Tonemapping` (src/app.rs:20-28)
+TONEMAPS = ["none", "reinhard", "aces_narkowicz", "aces_narkowicz_overexposed", "aces_hill", "neutral", "uncharted"]
 
 # every symbol the headers declare (tests check the library exports each of them)
 HOST_SYMBOLS = ["rpt_build_bvh", "rpt_build_light_pick_table", "rpt_pack_per_vertex", "rpt_make_rng_seeds", "rpt_camera_matrix",
@@ -25,7 +27,7 @@ HOST_SYMBOLS = ["rpt_build_bvh", "rpt_build_light_pick_table", "rpt_pack_per_ver
 DEVICE_SYMBOLS = [
     "rpt_create", "rpt_destroy", "rpt_last_error", "rpt_set_pipeline", "rpt_set_wave_slots", "rpt_upload_world",
     "rpt_set_config", "rpt_write_rng", "rpt_read_rng", "rpt_write_output", "rpt_set_tile_partition", "rpt_enqueue",
-    "rpt_sync", "rpt_read_output", "rpt_read_framebuffer", "rpt_read_primary_ids", "rpt_get_counters",
+    "rpt_sync", "rpt_read_output", "rpt_read_framebuffer", "rpt_read_display", "rpt_read_display_rgba8", "rpt_read_primary_ids", "rpt_get_counters",
     "rpt_reset_counters", "rpt_get_device_ms", "rpt_set_stage_timing", "rpt_get_stage_timing", "rpt_comm_unique_id", "rpt_comm_init", "rpt_comm_reduce_output",
     "rpt_comm_destroy", "rpt_host_alloc", "rpt_host_free",
 ]

@@ -127,6 +127,7 @@ struct rpt_context {
     DevBuf<uint2> d_rng;
     DevBuf<float4> d_output;
     DevBuf<float> d_rgb;
+    DevBuf<uint32_t> d_rgba8;
     DevBuf<uint32_t> d_ids;
     bool rng_written = false;
     uint32_t tile_rank = 0, tile_count = 1;
@@ -482,7 +483,7 @@ extern "C" int rpt_destroy(rpt_context* c) {
     c->w_qshadow.release(); c->w_ctl.release();
     c->d_counters.release(); c->d_vertices.release(); c->d_triangles.release(); c->d_nodes.release(); c->d_materials.release();
     c->d_lights.release(); c->d_atlas.release(); c->d_wide_nodes.release(); c->d_light_bins.release(); c->d_light_records.release();
-    c->d_rng.release(); c->d_rgb.release(); c->d_ids.release(); c->d_pixel_map.release();
+    c->d_rng.release(); c->d_rgb.release(); c->d_rgba8.release(); c->d_ids.release(); c->d_pixel_map.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RPT_OK;
@@ -670,6 +671,7 @@ extern "C" int rpt_set_config(rpt_context* c, const RptTracingConfig* cfg) {
         RPT_CUDA(c, c->d_output.alloc(n));
         RPT_CUDA(c, cudaMemsetAsync(c->d_output.p, 0, n * sizeof(float4), c->stream));
         c->d_rgb.release();
+        c->d_rgba8.release();
         c->d_ids.release();
         c->rng_written = false;
         RPT_TRY(rebuild_pixel_map(c));
@@ -792,6 +794,32 @@ extern "C" int rpt_read_framebuffer(rpt_context* c, float* rgb, size_t npixels, 
     RPT_CUDA(c, cudaGetLastError());
     RPT_CUDA(c, cudaMemcpyAsync(rgb, c->d_rgb.p, npixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     return c->cuda(cudaStreamSynchronize(c->stream), "rpt_read_framebuffer");
+}
+
+extern "C" int rpt_read_display(rpt_context* c, float* rgb, size_t npixels, float samples, uint32_t tonemap) {
+    if (!c || !rgb) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "rpt_read_display before rpt_set_config");
+    if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "frame has %u pixels, caller asked for %zu", c->npixels(), npixels);
+    RPT_TRY(bind_device(c));
+    if (c->d_rgb.n != npixels * 3) RPT_CUDA(c, c->d_rgb.alloc(npixels * 3));
+    launch_display(c->d_output.p, c->d_rgb.p, (uint32_t)npixels, samples, tonemap, c->stream);
+    c->kernel_launches++;
+    RPT_CUDA(c, cudaGetLastError());
+    RPT_CUDA(c, cudaMemcpyAsync(rgb, c->d_rgb.p, npixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    return c->cuda(cudaStreamSynchronize(c->stream), "rpt_read_display");
+}
+
+extern "C" int rpt_read_display_rgba8(rpt_context* c, uint8_t* rgba, size_t npixels, float samples, uint32_t tonemap, uint32_t srgb_encode) {
+    if (!c || !rgba) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "rpt_read_display_rgba8 before rpt_set_config");
+    if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "frame has %u pixels, caller asked for %zu", c->npixels(), npixels);
+    RPT_TRY(bind_device(c));
+    if (c->d_rgba8.n != npixels) RPT_CUDA(c, c->d_rgba8.alloc(npixels));
+    launch_display_rgba8(c->d_output.p, c->d_rgba8.p, (uint32_t)npixels, samples, tonemap, srgb_encode != 0, c->stream);
+    c->kernel_launches++;
+    RPT_CUDA(c, cudaGetLastError());
+    RPT_CUDA(c, cudaMemcpyAsync(rgba, c->d_rgba8.p, npixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    return c->cuda(cudaStreamSynchronize(c->stream), "rpt_read_display_rgba8");
 }
 
 extern "C" int rpt_read_primary_ids(rpt_context* c, uint32_t* ids, size_t npixels) {

@@ -125,6 +125,8 @@ void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld&
 void launch_wf_compact_shaded(const WaveLaunch& l, const WaveState& s, int out_queue);
 void launch_wf_miss(const WaveLaunch& l, const FrameParams& f, const WaveState& s);
 void launch_wf_accumulate(const WaveLaunch& l, const WaveState& s, const WaveDesc& d, uint2* rng, float4* output);
-void launch_normalize(const float4* output, float* rgb, uint32_t npixels, float samples, cudaStream_t stream);
+void launch_normalize(const float4* output, float* rgb, uint32_t npixels, float samples, cudaStream_t stream);  // display_nofma.cu
+void launch_display(const float4* output, float* rgb, uint32_t npixels, float samples, uint32_t tonemap_op, cudaStream_t stream);
+void launch_display_rgba8(const float4* output, uint32_t* rgba8, uint32_t npixels, float samples, uint32_t tonemap_op, bool srgb, cudaStream_t stream);
 
 }  // namespace rpt

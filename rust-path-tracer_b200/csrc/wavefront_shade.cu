@@ -220,15 +220,6 @@ __global__ void wf_reset_kernel(WaveState s, int next_queue, bool whole) {
     }
 }
 
-__global__ void normalize_kernel(const float4* __restrict__ output, float* __restrict__ rgb, uint32_t npixels, float samples) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npixels) return;
-    const float4 c = output[i];
-    rgb[3 * (size_t)i + 0] = c.x / samples;
-    rgb[3 * (size_t)i + 1] = c.y / samples;
-    rgb[3 * (size_t)i + 2] = c.z / samples;
-}
-
 void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld& w, const WaveState& s, const WaveDesc& d, const uint2* rng,
                      uint32_t bounce) {
     if (w.nmaterials <= kSmemMaterials) wf_shade_kernel<true><<<l.grid * 4, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce);
@@ -240,9 +231,6 @@ void launch_wf_miss_procedural(const WaveLaunch& l, const FrameParams& f, const 
 }
 void launch_wf_accumulate(const WaveLaunch& l, const WaveState& s, const WaveDesc& d, uint2* rng, float4* output) {
     wf_accumulate_kernel<<<l.grid * 8, 256, 0, l.stream>>>(s, d, rng, output);
-}
-void launch_normalize(const float4* output, float* rgb, uint32_t npixels, float samples, cudaStream_t stream) {
-    normalize_kernel<<<(npixels + 255) / 256, 256, 0, stream>>>(output, rgb, npixels, samples);
 }
 
 }  // namespace rpt

@@ -28,6 +28,10 @@ from .capi import TracingConfig
 from .world import World, make_rng_seeds
 
 
+def _tonemap_index(tonemap) -> int:
+    return capi.TONEMAPS.index(tonemap) if isinstance(tonemap, str) else int(tonemap)
+
+
 class Renderer:
     """One CUDA tracing context (one GPU).  Raises capi.RptError on any failure."""
 
@@ -123,6 +127,21 @@ class Renderer:
         if out is None:
             out = np.empty(self.npixels * 3, np.float32)
         self._call("rpt_read_framebuffer", capi.ptr(out), C.c_size_t(self.npixels), C.c_float(samples))
+        return out
+
+    def read_display(self, samples: float, tonemap: int | str = 0, out: np.ndarray | None = None) -> np.ndarray:
+        """render.wgsl's fragment stage on the device: packed RGB f32 of tonemap(output.xyz / samples)."""
+        if out is None:
+            out = np.empty(self.npixels * 3, np.float32)
+        self._call("rpt_read_display", capi.ptr(out), C.c_size_t(self.npixels), C.c_float(samples), C.c_uint32(_tonemap_index(tonemap)))
+        return out
+
+    def read_display_rgba8(self, samples: float, tonemap: int | str = 0, srgb: bool = True, out: np.ndarray | None = None) -> np.ndarray:
+        """What save_render writes (src/app.rs:759-840): (npixels, 4) bytes R,G,B,255 of the tonemapped frame."""
+        if out is None:
+            out = np.empty((self.npixels, 4), np.uint8)
+        self._call("rpt_read_display_rgba8", capi.ptr(out), C.c_size_t(self.npixels), C.c_float(samples), C.c_uint32(_tonemap_index(tonemap)),
+                   C.c_uint32(1 if srgb else 0))
         return out
 
     def read_primary_ids(self) -> np.ndarray:
