@@ -159,4 +159,24 @@ int harness_wide_intersect(const RptPerVertexData* verts, uint32_t nverts, const
     }
     return 0;
 }
+// Digest of the collapsed tree (FNV-1a over nodes, triangle records and both index maps) + its counts:
+// out[0] digest low, [1] digest high, [2] nodes, [3] max depth, [4] inner children, [5] leaf children.
+int harness_wide_digest(const RptPerVertexData* verts, uint32_t nverts, const uint32_t* tris, uint32_t ntris, const RptBVHNode* nodes,
+                        uint32_t nnodes, uint32_t* out) {
+    rpt::WideBvh wide;
+    const char* err = "";
+    if (!rpt::build_wide_bvh(nodes, nnodes, tris, ntris, verts, nverts, wide, &err)) return -1;
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](const void* p, size_t bytes) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    mix(wide.nodes.data(), wide.nodes.size() * sizeof(rpt::WideNode));
+    mix(wide.tri_pos.data(), wide.tri_pos.size() * sizeof(float));
+    mix(wide.orig_index.data(), wide.orig_index.size() * sizeof(uint32_t));
+    mix(wide.wide_index.data(), wide.wide_index.size() * sizeof(uint32_t));
+    out[0] = (uint32_t)h; out[1] = (uint32_t)(h >> 32);
+    out[2] = (uint32_t)wide.nodes.size(); out[3] = wide.max_depth; out[4] = wide.inner_children; out[5] = wide.leaf_children;
+    return 0;
+}
 }

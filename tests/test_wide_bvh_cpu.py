@@ -21,7 +21,7 @@ def harness():
     hdrs = [os.path.join(helpers.REPO, "rust-path-tracer_b200", "csrc", "dev", h) for h in ("wide_bvh.cuh", "exact.cuh", "vec.cuh")]
     os.makedirs(os.path.dirname(HARNESS_SO), exist_ok=True)
     if not os.path.exists(HARNESS_SO) or any(os.path.getmtime(s) > os.path.getmtime(HARNESS_SO) for s in srcs + hdrs):
-        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-o", HARNESS_SO, *srcs], check=True,
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", HARNESS_SO, *srcs], check=True,
                        capture_output=True)
     return C.CDLL(HARNESS_SO)
 
@@ -97,3 +97,43 @@ def test_unorm8_is_the_ieee_division(harness):
     got = np.array([harness.harness_unorm8(C.c_uint32(x)) for x in range(256)], np.float32)
     want = np.arange(256, dtype=np.float32) / np.float32(255.0)
     np.testing.assert_array_equal(got, want)
+
+
+def wide_digest(lib, world, nodes=None):
+    nodes = world.nodes if nodes is None else nodes
+    out = np.zeros(6, np.uint32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.harness_wide_digest(P(world.per_vertex_buffer), C.c_uint32(len(world.per_vertex_buffer)), P(world.index_buffer),
+                                 C.c_uint32(len(world.index_buffer)), P(nodes), C.c_uint32(len(nodes)), P(out))
+    return rc, out.tolist()
+
+
+@pytest.mark.parametrize("mode", ["dp", "greedy"])
+def test_collapse_is_independent_of_thread_count(harness, mode, monkeypatch):
+    """The collapse builds every level of the wide tree with all host threads; nodes, triangle records and both
+    index maps must come out bit for bit the same for any thread count."""
+    world = helpers.world("PBRTest")  # 47 k binary nodes: large enough to be shared out
+    monkeypatch.setenv("RPT_COLLAPSE", mode)
+    digests = []
+    for threads in ("1", "2", "5", "16"):
+        monkeypatch.setenv("RPT_BUILD_THREADS", threads)
+        rc, d = wide_digest(harness, world)
+        assert rc == 0
+        digests.append(d)
+    assert all(d == digests[0] for d in digests), digests
+
+
+def test_collapse_rejects_malformed_trees(harness, monkeypatch):
+    world = helpers.world("PBRTest")
+    inner = np.flatnonzero(world.nodes["triangle_count"] == 0)
+    for threads in ("1", "8"):
+        monkeypatch.setenv("RPT_BUILD_THREADS", threads)
+        bad = world.nodes.copy()
+        bad["left_or_first"][inner[-1]] = len(bad) - 1          # right child out of range
+        assert wide_digest(harness, world, bad)[0] == -1
+        bad = world.nodes.copy()
+        bad["left_or_first"][inner[-1]] = bad["left_or_first"][inner[10]]  # a subtree referenced twice (and its own orphaned)
+        assert wide_digest(harness, world, bad)[0] == -1
+        bad = world.nodes.copy()
+        bad["left_or_first"][inner[-1]] = 0                     # a cycle through the root
+        assert wide_digest(harness, world, bad)[0] == -1
