@@ -14,6 +14,7 @@
 #include <cstring>
 #include <future>
 #include <limits>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -29,8 +30,15 @@ struct F3 {
     float operator[](int a) const { return a == 0 ? x : (a == 1 ? y : z); }
 };
 inline F3 f3(const float* p) { return {p[0], p[1], p[2]}; }
-inline F3 vmin(F3 a, F3 b) { return {std::fmin(a.x, b.x), std::fmin(a.y, b.y), std::fmin(a.z, b.z)}; }
-inline F3 vmax(F3 a, F3 b) { return {std::fmax(a.x, b.x), std::fmax(a.y, b.y), std::fmax(a.z, b.z)}; }
+// fminf / fmaxf (NaN-ignoring, like Rust's f32::min / max) written out: without -ffast-math the compiler calls into
+// libm for every one of them, and the builder does a few hundred million.
+inline float min_f(float x, float y) { return x < y ? x : (x > y ? y : (y != y ? x : y)); }
+inline float max_f(float x, float y) { return x > y ? x : (x < y ? y : (y != y ? x : y)); }
+// The same when the first operand is a running bound (+-inf or a value, never NaN): one compare and a select.
+inline float acc_min(float acc, float y) { return y <= acc ? y : acc; }
+inline float acc_max(float acc, float y) { return y >= acc ? y : acc; }
+inline F3 vmin(F3 a, F3 b) { return {min_f(a.x, b.x), min_f(a.y, b.y), min_f(a.z, b.z)}; }
+inline F3 vmax(F3 a, F3 b) { return {max_f(a.x, b.x), max_f(a.y, b.y), max_f(a.z, b.z)}; }
 inline F3 sub(F3 a, F3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 inline float length(F3 a) { return std::sqrt((a.x * a.x + a.y * a.y) + a.z * a.z); }
 
@@ -38,11 +46,13 @@ inline float length(F3 a) { return std::sqrt((a.x * a.x + a.y * a.y) + a.z * a.z
 struct Box {
     F3 lo{kInf, kInf, kInf};
     F3 hi{-kInf, -kInf, -kInf};
-    void grow(F3 p) { lo = vmin(lo, p); hi = vmax(hi, p); }
+    void grow(F3 l, F3 h) {  // by a box whose bounds may hold NaN (ignored)
+        lo = {acc_min(lo.x, l.x), acc_min(lo.y, l.y), acc_min(lo.z, l.z)};
+        hi = {acc_max(hi.x, h.x), acc_max(hi.y, h.y), acc_max(hi.z, h.z)};
+    }
     void grow(const Box& b) {
         if (b.lo.x == kInf) return;  // src/bvh.rs:21-27: empty bins are skipped
-        lo = vmin(lo, b.lo);
-        hi = vmax(hi, b.hi);
+        grow(b.lo, b.hi);
     }
     // src/bvh.rs:29-32 — half the surface area; an empty box evaluates to +inf
     float half_area() const {
@@ -58,15 +68,23 @@ struct Tri { uint32_t i0, i1, i2, mat; };
 // the array is laid out as  [X, l, r, descendants(l)..., descendants(r)...]  recursively.  A subtree therefore
 // depends on nothing but its own triangle range, and its nodes are contiguous once the size of everything before
 // it is known: the big subtrees near the root are built by concurrent tasks into local arrays (indices relative to
-// the subtree's root) and spliced together afterwards — same nodes, same order, same permutation of the index
+// the subtree's root) and copied to their places afterwards — same nodes, same order, same permutation of the index
 // buffer as the sequential build, in a fraction of the time (1 M triangles: 11.7 s -> ~1.5 s on 16 cores).
 class SahBuilder {
   public:
-    SahBuilder(const float* verts, Tri* tris, uint32_t ntris, uint32_t bins) : verts_(verts), tris_(tris), ntris_(ntris), bins_(bins), centroids_(ntris) {
-        for (uint32_t t = 0; t < ntris; ++t) {  // src/bvh.rs:60-68
+    SahBuilder(const float* verts, Tri* tris, uint32_t ntris, uint32_t bins) : verts_(verts), tris_(tris), ntris_(ntris), bins_(bins), recs_(ntris) {
+        unsigned threads = std::thread::hardware_concurrency();
+        if (const char* v = std::getenv("RPT_BUILD_THREADS")) threads = (unsigned)std::max(1, std::atoi(v));
+        run_chunks(ntris, ntris < kSharedNodeMinTriangles ? 1u : std::max(1u, threads), [&](unsigned, uint32_t begin, uint32_t end) {
+        for (uint32_t t = begin; t < end; ++t) {  // src/bvh.rs:60-68
             F3 a = pos(tris[t].i0), b = pos(tris[t].i1), c = pos(tris[t].i2);
-            centroids_[t] = {((a.x + b.x) + c.x) / 3.0f, ((a.y + b.y) + c.y) / 3.0f, ((a.z + b.z) + c.z) / 3.0f};
+            recs_[t].centroid = {((a.x + b.x) + c.x) / 3.0f, ((a.y + b.y) + c.y) / 3.0f, ((a.z + b.z) + c.z) / 3.0f};
+            // The reference grows boxes vertex by vertex; min and max are exact, so growing by the triangle's own box
+            // gives the same bits and spares three random vertex fetches per triangle, axis and tree level.
+            recs_[t].lo = vmin(vmin(a, b), c);
+            recs_[t].hi = vmax(vmax(a, b), c);
         }
+        });
     }
 
     // Nodes of the whole tree in the reference's order; nodes_out has room for 2 * ntris - 1.
@@ -75,21 +93,50 @@ class SahBuilder {
         if (const char* v = std::getenv("RPT_BUILD_THREADS")) threads = (unsigned)std::max(1, std::atoi(v));
         int fork_levels = 0;
         while ((1u << fork_levels) < std::max(1u, threads)) ++fork_levels;
-        const std::vector<RptBVHNode> nodes = build_subtree(0, ntris_, threads <= 1 ? 0 : fork_levels + 1);  // one thread: the reference's loop as is
-        std::memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(RptBVHNode));
-        return (uint32_t)nodes.size();
+        const std::unique_ptr<Piece> tree = build_subtree(0, ntris_, threads <= 1 ? 0 : fork_levels + 1, threads);  // one thread: the reference's loop as is
+        emit(*tree, nodes_out, 0, 1);
+        return (uint32_t)tree->size;
     }
 
   private:
-    struct Scratch {
+    // Centroid and box of a triangle, permuted together with the index buffer.
+    struct TriRec { F3 centroid, lo, hi; };
+
+    struct Scratch {  // bins of all three axes ([axis * bins + bin]) and the sweep tables of one axis
         std::vector<Box> seg_box;
-        std::vector<uint32_t> seg_count, left_count, right_count;
+        std::vector<uint32_t> seg_count, left_count, right_count, touched, tri_bin;
         std::vector<float> left_area, right_area;
-        explicit Scratch(uint32_t bins) : seg_box(bins), seg_count(bins), left_count(bins - 1), right_count(bins - 1), left_area(bins - 1), right_area(bins - 1) {}
+        bool dirty = false;
+        explicit Scratch(uint32_t bins)
+            : seg_box(3 * (size_t)bins), seg_count(3 * (size_t)bins, 0u), left_count(bins), right_count(bins), left_area(bins), right_area(bins) {
+            touched.reserve(bins);
+            tri_bin.resize(3 * (size_t)bins);
+        }
     };
     static constexpr uint32_t kForkMinTriangles = 8192;  // below this a task costs more than it saves
+    static constexpr uint32_t kSharedNodeMinTriangles = 1u << 16;  // a node this big is binned by several workers
+
+    // fn(worker, begin, end) over `workers` consecutive runs of [0, count); worker 0 is the caller.
+    template <class Fn>
+    static void run_chunks(uint32_t count, unsigned workers, Fn&& fn) {
+        if (workers <= 1) { fn(0u, 0u, count); return; }
+        std::vector<std::thread> pool;
+        pool.reserve(workers - 1);
+        auto bound = [&](unsigned w) { return (uint32_t)((uint64_t)count * w / workers); };
+        for (unsigned w = 1; w < workers; ++w) pool.emplace_back([&fn, &bound, w] { fn(w, bound(w), bound(w + 1)); });
+        fn(0u, 0u, bound(1));
+        for (std::thread& t : pool) t.join();
+    }
 
     F3 pos(uint32_t v) const { return f3(verts_ + 4 * (size_t)v); }
+    // `f as usize` (saturating: negative / NaN -> 0) followed by `.min(bins - 1)` (src/bvh.rs:203-204)
+    static uint32_t bin_of(float f, uint32_t bins) {
+        if (bins > (1u << 24)) {  // (float)bins would round: the literal form
+            const size_t b = f > 0.0f ? (f >= 1.8446744e19f ? SIZE_MAX : (size_t)f) : 0;
+            return (uint32_t)std::min<size_t>(b, bins - 1u);
+        }
+        return f > 0.0f ? (f >= (float)bins ? bins - 1u : (uint32_t)(int32_t)f) : 0u;
+    }
     static float node_half_area(const RptBVHNode& n) {
         Box b;
         b.lo = f3(n.aabb_min);
@@ -98,35 +145,61 @@ class SahBuilder {
     }
     static RptBVHNode leaf(uint32_t first, uint32_t count) { return RptBVHNode{{kInf, kInf, kInf}, count, {-kInf, -kInf, -kInf}, first}; }
 
-    // [root, l, r, descendants(l), descendants(r)] of the subtree over triangles [first, first + count); inner
-    // nodes hold the index of their left child RELATIVE to the subtree's root.
-    std::vector<RptBVHNode> build_subtree(uint32_t first, uint32_t count, int fork_levels) {
-        if (fork_levels <= 0 || count < kForkMinTriangles) return build_sequential(first, count);
+    // A subtree as the concurrent build leaves it: either one array built by the reference's loop (child indices
+    // relative to the subtree's root), or a root whose two halves were built by separate tasks.
+    struct Piece {
+        std::vector<RptBVHNode> flat;
+        RptBVHNode root;
+        std::unique_ptr<Piece> left, right;
+        size_t size = 0;
+    };
+
+    // `workers`: host threads this subtree may use for its own root (its two halves get half of them each).
+    std::unique_ptr<Piece> build_subtree(uint32_t first, uint32_t count, int fork_levels, unsigned workers) {
+        auto piece = std::make_unique<Piece>();
+        if (fork_levels <= 0 || count < kForkMinTriangles) {
+            piece->flat = build_sequential(first, count);
+            piece->size = piece->flat.size();
+            return piece;
+        }
         Scratch scratch(bins_);
-        RptBVHNode root = leaf(first, count);
-        fit(root);
+        piece->root = leaf(first, count);
+        fit(piece->root, workers);
         uint32_t left_n = 0;
-        if (!split(root, scratch, left_n)) return {root};
-        auto left_task = std::async(std::launch::async, [=] { return build_subtree(first, left_n, fork_levels - 1); });
-        const std::vector<RptBVHNode> right = build_subtree(first + left_n, count - left_n, fork_levels - 1);
-        const std::vector<RptBVHNode> left = left_task.get();
-        // splice: L[0] -> 1, R[0] -> 2, L[j >= 1] -> j + 2, R[j >= 1] -> |L| + 1 + j; child indices (always >= 1) move alike
-        std::vector<RptBVHNode> out;
-        out.reserve(1 + left.size() + right.size());
+        if (!split(piece->root, scratch, left_n, workers)) {
+            piece->flat = {piece->root};
+            piece->size = 1;
+            return piece;
+        }
+        const unsigned half = std::max(1u, workers / 2);
+        auto left_task = std::async(std::launch::async, [=] { return build_subtree(first, left_n, fork_levels - 1, half); });
+        piece->right = build_subtree(first + left_n, count - left_n, fork_levels - 1, half);
+        piece->left = left_task.get();
+        piece->size = 1 + piece->left->size + piece->right->size;
+        return piece;
+    }
+
+    // Writes a piece where the reference's single loop would have put it: the subtree's root at `root_at`, then
+    // [l, r, descendants(l)..., descendants(r)...] from `rest_at` on (every node is copied once, the big pieces by
+    // tasks of their own).
+    void emit(const Piece& piece, RptBVHNode* out, size_t root_at, size_t rest_at) const {
+        if (!piece.left) {
+            const std::vector<RptBVHNode>& flat = piece.flat;
+            for (size_t j = 0; j < flat.size(); ++j) {
+                RptBVHNode n = flat[j];
+                if (n.triangle_count == 0) n.left_or_first += (uint32_t)rest_at - 1u;  // relative child index c >= 1 -> rest_at + c - 1
+                out[j == 0 ? root_at : rest_at + j - 1] = n;
+            }
+            return;
+        }
+        RptBVHNode root = piece.root;
         root.triangle_count = 0;
-        root.left_or_first = 1;
-        out.push_back(root);
-        out.push_back(left[0]);
-        out.push_back(right[0]);
-        out.insert(out.end(), left.begin() + 1, left.end());
-        out.insert(out.end(), right.begin() + 1, right.end());
-        const uint32_t nl = (uint32_t)left.size();
-        auto shift = [&](size_t at, uint32_t by) { if (out[at].triangle_count == 0) out[at].left_or_first += by; };
-        shift(1, 2);
-        shift(2, nl + 1);
-        for (size_t j = 1; j < left.size(); ++j) shift(2 + j, 2);
-        for (size_t j = 1; j < right.size(); ++j) shift(1 + nl + j, nl + 1);
-        return out;
+        root.left_or_first = (uint32_t)rest_at;
+        out[root_at] = root;
+        const size_t left_rest = rest_at + 2, right_rest = left_rest + (piece.left->size - 1);
+        auto left_task = std::async(std::launch::async, [=, &piece] { emit(*piece.left, out, rest_at, left_rest); });
+        emit(*piece.right, out, rest_at + 1, right_rest);
+        left_task.get();
     }
 
     // The reference's loop, src/bvh.rs:257-323, on one subtree.
@@ -157,10 +230,10 @@ class SahBuilder {
     }
 
     // Decides whether `node` (a leaf over its triangle range) is split and, if so, partitions the range in place.
-    bool split(const RptBVHNode& node, Scratch& scratch, uint32_t& left_n) {
+    bool split(const RptBVHNode& node, Scratch& scratch, uint32_t& left_n, unsigned workers = 1) {
         int axis;
         float plane, cost;
-        best_split(node, scratch, axis, plane, cost);
+        best_split(node, scratch, workers, axis, plane, cost);
         const float keep_cost = node_half_area(node) * (float)node.triangle_count;
         if (keep_cost <= cost) return false;
         // in-place partition of [first, first+count) around the plane; 64-bit cursors so the
@@ -168,11 +241,11 @@ class SahBuilder {
         int64_t a = node.left_or_first;
         int64_t b = (int64_t)node.left_or_first + node.triangle_count - 1;
         while (a <= b) {
-            if (centroids_[a][axis] < plane) {
+            if (recs_[a].centroid[axis] < plane) {
                 ++a;
             } else {
                 std::swap(tris_[a], tris_[b]);
-                std::swap(centroids_[a], centroids_[b]);
+                std::swap(recs_[a], recs_[b]);
                 --b;
             }
         }
@@ -180,70 +253,160 @@ class SahBuilder {
         return left_n != 0 && left_n != node.triangle_count;
     }
 
-    void fit(RptBVHNode& n) const {  // src/bvh.rs:91-110
+    void fit(RptBVHNode& n, unsigned workers = 1) const {  // src/bvh.rs:91-110
+        if (n.triangle_count < kSharedNodeMinTriangles) workers = 1;
+        std::vector<Box> part(workers);
+        run_chunks(n.triangle_count, workers, [&](unsigned w, uint32_t begin, uint32_t end) {
+            Box b;
+            for (uint32_t k = begin; k < end; ++k) {
+                const TriRec& r = recs_[n.left_or_first + k];
+                b.grow(r.lo, r.hi);
+            }
+            part[w] = b;
+        });
         Box box;
-        for (uint32_t k = 0; k < n.triangle_count; ++k) {
-            const Tri& t = tris_[n.left_or_first + k];
-            F3 a = pos(t.i0), b = pos(t.i1), c = pos(t.i2);
-            box.lo = vmin(box.lo, vmin(vmin(a, b), c));
-            box.hi = vmax(box.hi, vmax(vmax(a, b), c));
-        }
+        for (const Box& b : part) box.grow(b.lo, b.hi);
         n.aabb_min[0] = box.lo.x; n.aabb_min[1] = box.lo.y; n.aabb_min[2] = box.lo.z;
         n.aabb_max[0] = box.hi.x; n.aabb_max[1] = box.hi.y; n.aabb_max[2] = box.hi.z;
     }
 
-    // src/bvh.rs:178-255 — binned sweep; candidate planes sit between adjacent bins
-    void best_split(const RptBVHNode& node, Scratch& sc, int& best_axis, float& best_plane, float& best_cost) const {
+    // src/bvh.rs:178-255 — binned sweep; candidate planes sit between adjacent bins.  The reference walks the
+    // triangles once per axis and sweeps all bins of every node; here the three axes are binned in one pass and a node
+    // with fewer triangles than bins sweeps only the bins it filled.  Same result, bit for bit: a plane that follows an
+    // empty bin has the counts and boxes — hence the cost — of the plane before it, which the strict `<` already
+    // prefers, and a plane with nothing on one side costs 0 * inf = NaN, which never wins.
+    void best_split(const RptBVHNode& node, Scratch& sc, unsigned workers, int& best_axis, float& best_plane, float& best_cost) const {
         best_axis = 0;
         best_plane = 0.0f;
         best_cost = kInf;
         const uint32_t first = node.left_or_first, count = node.triangle_count;
         const uint32_t nb = bins_;
-        for (int axis = 0; axis < 3; ++axis) {
-            float lo = kInf, hi = -kInf;
-            for (uint32_t k = 0; k < count; ++k) {
-                const float c = centroids_[first + k][axis];
-                lo = std::fmin(lo, c);
-                hi = std::fmax(hi, c);
-            }
-            if (lo == hi) continue;
+        const TriRec* recs = recs_.data() + first;
 
+        // Big nodes near the root are shared by the workers this subtree owns: each takes a run of the triangles, and
+        // the partial bounds, boxes and counts are merged in run order — min / max / + give the sequential result exactly
+        // (a tie between +0 and -0 goes to the later triangle either way).
+        if (workers > 1 && count < kSharedNodeMinTriangles) workers = 1;
+        float lo[3] = {kInf, kInf, kInf}, hi[3] = {-kInf, -kInf, -kInf};
+        {
+            std::vector<float> part(6 * (size_t)workers);
+            run_chunks(count, workers, [&](unsigned w, uint32_t begin, uint32_t end) {
+                float l[3] = {kInf, kInf, kInf}, h[3] = {-kInf, -kInf, -kInf};
+                for (uint32_t k = begin; k < end; ++k) {
+                    const F3 c = recs[k].centroid;
+                    l[0] = acc_min(l[0], c.x); h[0] = acc_max(h[0], c.x);
+                    l[1] = acc_min(l[1], c.y); h[1] = acc_max(h[1], c.y);
+                    l[2] = acc_min(l[2], c.z); h[2] = acc_max(h[2], c.z);
+                }
+                for (int a = 0; a < 3; ++a) { part[6 * (size_t)w + a] = l[a]; part[6 * (size_t)w + 3 + a] = h[a]; }
+            });
+            for (unsigned w = 0; w < workers; ++w)
+                for (int a = 0; a < 3; ++a) { lo[a] = acc_min(lo[a], part[6 * (size_t)w + a]); hi[a] = acc_max(hi[a], part[6 * (size_t)w + 3 + a]); }
+        }
+        float to_bin[3];
+        bool live[3];
+        for (int axis = 0; axis < 3; ++axis) {
+            live[axis] = !(lo[axis] == hi[axis]);
+            to_bin[axis] = (float)nb / (hi[axis] - lo[axis]);
+        }
+        const bool sparse = count < nb;  // a sparse node empties the bins it filled; a dense one leaves them for the next node to clear
+        if (!sparse || sc.dirty) {
             std::fill(sc.seg_box.begin(), sc.seg_box.end(), Box{});
             std::fill(sc.seg_count.begin(), sc.seg_count.end(), 0u);
-            const float to_bin = (float)nb / (hi - lo);
-            for (uint32_t k = 0; k < count; ++k) {
-                const Tri& t = tris_[first + k];
-                const float f = (centroids_[first + k][axis] - lo) * to_bin;
-                // Rust `as usize` saturates: negative / NaN -> 0
-                size_t bin = (f > 0.0f) ? (f >= 1.8446744e19f ? SIZE_MAX : (size_t)f) : 0;
-                bin = std::min<size_t>(bin, nb - 1);
-                sc.seg_box[bin].grow(pos(t.i0));
-                sc.seg_box[bin].grow(pos(t.i1));
-                sc.seg_box[bin].grow(pos(t.i2));
-                sc.seg_count[bin] += 1;
-            }
+        }
+        sc.dirty = !sparse;
+        {
+            std::vector<Box> part_box((size_t)(workers - 1) * 3 * nb);
+            std::vector<uint32_t> part_count((size_t)(workers - 1) * 3 * nb, 0u);
+            run_chunks(count, workers, [&](unsigned w, uint32_t begin, uint32_t end) {
+                Box* seg_box = w == 0 ? sc.seg_box.data() : part_box.data() + (size_t)(w - 1) * 3 * nb;
+                uint32_t* seg_count = w == 0 ? sc.seg_count.data() : part_count.data() + (size_t)(w - 1) * 3 * nb;
+                for (uint32_t k = begin; k < end; ++k) {
+                    const TriRec& r = recs[k];
+                    for (int axis = 0; axis < 3; ++axis) {
+                        if (!live[axis]) continue;
+                        const uint32_t b = bin_of((r.centroid[axis] - lo[axis]) * to_bin[axis], nb);
+                        if (sparse) sc.tri_bin[(size_t)axis * nb + k] = b;
+                        const size_t bin = b + (size_t)axis * nb;
+                        seg_box[bin].grow(r.lo, r.hi);
+                        seg_count[bin] += 1;
+                    }
+                }
+            });
+            for (unsigned w = 1; w < workers; ++w)
+                for (size_t bin = 0; bin < 3 * (size_t)nb; ++bin) {
+                    const size_t at = (size_t)(w - 1) * 3 * nb + bin;
+                    sc.seg_box[bin].grow(part_box[at].lo, part_box[at].hi);
+                    sc.seg_count[bin] += part_count[at];
+                }
+        }
 
+        for (int axis = 0; axis < 3; ++axis) {
+            if (!live[axis]) continue;
+            const Box* seg_box = sc.seg_box.data() + (size_t)axis * nb;
+            const uint32_t* seg_count = sc.seg_count.data() + (size_t)axis * nb;
+            const float step = (hi[axis] - lo[axis]) / (float)nb;
+            if (!sparse) {
+                Box lbox, rbox;
+                uint32_t lsum = 0, rsum = 0;
+                for (uint32_t i = 0; i + 1 < nb; ++i) {
+                    lsum += seg_count[i];
+                    sc.left_count[i] = lsum;
+                    lbox.grow(seg_box[i]);
+                    sc.left_area[i] = lbox.half_area();
+                    rsum += seg_count[nb - 1 - i];
+                    sc.right_count[nb - 2 - i] = rsum;
+                    rbox.grow(seg_box[nb - 1 - i]);
+                    sc.right_area[nb - 2 - i] = rbox.half_area();
+                }
+                for (uint32_t i = 0; i + 1 < nb; ++i) {
+                    const float c = (float)sc.left_count[i] * sc.left_area[i] + (float)sc.right_count[i] * sc.right_area[i];
+                    if (c < best_cost) {
+                        best_axis = axis;
+                        best_plane = lo[axis] + step * (float)(i + 1);
+                        best_cost = c;
+                    }
+                }
+                continue;
+            }
+            // the filled bins in ascending order (at least two: the smallest centroid is in bin 0, the largest in the last)
+            sc.touched.clear();
+            if (count <= 16) {  // a handful of triangles: sort their bins (insertion, dropping repeats)
+                const uint32_t* tb = sc.tri_bin.data() + (size_t)axis * nb;
+                for (uint32_t k = 0; k < count; ++k) {
+                    size_t at = sc.touched.size();
+                    while (at > 0 && sc.touched[at - 1] > tb[k]) --at;
+                    if (at > 0 && sc.touched[at - 1] == tb[k]) continue;
+                    sc.touched.insert(sc.touched.begin() + at, tb[k]);
+                }
+            } else {
+                for (uint32_t i = 0; i < nb; ++i)
+                    if (seg_count[i] != 0) sc.touched.push_back(i);
+            }
+            const uint32_t m = (uint32_t)sc.touched.size();
             Box lbox, rbox;
             uint32_t lsum = 0, rsum = 0;
-            for (uint32_t i = 0; i + 1 < nb; ++i) {
-                lsum += sc.seg_count[i];
-                sc.left_count[i] = lsum;
-                lbox.grow(sc.seg_box[i]);
-                sc.left_area[i] = lbox.half_area();
-                rsum += sc.seg_count[nb - 1 - i];
-                sc.right_count[nb - 2 - i] = rsum;
-                rbox.grow(sc.seg_box[nb - 1 - i]);
-                sc.right_area[nb - 2 - i] = rbox.half_area();
+            for (uint32_t j = 0; j + 1 < m; ++j) {  // entry j: the plane right after filled bin j
+                lsum += seg_count[sc.touched[j]];
+                sc.left_count[j] = lsum;
+                lbox.grow(seg_box[sc.touched[j]]);
+                sc.left_area[j] = lbox.half_area();
+                rsum += seg_count[sc.touched[m - 1 - j]];
+                sc.right_count[m - 2 - j] = rsum;
+                rbox.grow(seg_box[sc.touched[m - 1 - j]]);
+                sc.right_area[m - 2 - j] = rbox.half_area();
             }
-
-            const float step = (hi - lo) / (float)nb;
-            for (uint32_t i = 0; i + 1 < nb; ++i) {
-                const float c = (float)sc.left_count[i] * sc.left_area[i] + (float)sc.right_count[i] * sc.right_area[i];
+            for (uint32_t j = 0; j + 1 < m; ++j) {
+                const float c = (float)sc.left_count[j] * sc.left_area[j] + (float)sc.right_count[j] * sc.right_area[j];
                 if (c < best_cost) {
                     best_axis = axis;
-                    best_plane = lo + step * (float)(i + 1);
+                    best_plane = lo[axis] + step * (float)(sc.touched[j] + 1);
                     best_cost = c;
                 }
+            }
+            for (uint32_t bin : sc.touched) {  // leave the bins clean
+                sc.seg_box[(size_t)axis * nb + bin] = Box{};
+                sc.seg_count[(size_t)axis * nb + bin] = 0u;
             }
         }
     }
@@ -252,7 +415,7 @@ class SahBuilder {
     Tri* tris_;
     uint32_t ntris_;
     uint32_t bins_;
-    std::vector<F3> centroids_;
+    std::vector<TriRec> recs_;
 };
 
 // src/light_pick.rs:5-11 — Heron's formula
