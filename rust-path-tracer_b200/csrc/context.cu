@@ -17,6 +17,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <thread>
 #include <vector>
 
 #include "../../include/rpt_b200.h"
@@ -505,6 +506,22 @@ extern "C" int rpt_set_wave_slots(rpt_context* c, uint32_t slots) {
 }
 
 // ============================================================================ scene
+namespace {
+// fn(begin, end) over consecutive runs of [0, n) on the host threads (RPT_BUILD_THREADS, like the BVH builders).
+template <class Fn>
+void host_parallel_for(uint32_t n, Fn&& fn) {
+    unsigned threads = std::max(1u, std::thread::hardware_concurrency());
+    if (const char* v = getenv("RPT_BUILD_THREADS")) threads = (unsigned)std::max(1, atoi(v));
+    threads = std::min<unsigned>(threads, n / 65536u);  // small scenes: not worth a thread launch
+    if (threads <= 1) { fn(0u, n); return; }
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < threads; ++w)
+        pool.emplace_back([&fn, n, w, threads] { fn((uint32_t)((uint64_t)n * w / threads), (uint32_t)((uint64_t)n * (w + 1) / threads)); });
+    fn(0u, (uint32_t)((uint64_t)n / threads));
+    for (std::thread& t : pool) t.join();
+}
+}  // namespace
+
 extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices, uint32_t nvertices, const uint32_t* triangles,
                                 uint32_t ntriangles, const RptBVHNode* nodes, uint32_t nnodes, const RptMaterialData* materials,
                                 uint32_t nmaterials, const RptLightPickEntry* lights, uint32_t nlights, const uint8_t* atlas_rgba8,
@@ -537,21 +554,26 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     }();
     if (textured && !atlas_rgba8) return c->fail(RPT_ERR_INVALID_ARGUMENT, "a material is textured but no atlas was supplied");
 
-    std::vector<float> shade((size_t)ntriangles * 16), tangent(any_normal_map ? (size_t)ntriangles * 12 : 0);
-    for (uint32_t wi = 0; wi < ntriangles; ++wi) {
-        const uint32_t* tri = triangles + 4 * (size_t)wide.orig_index[wi];
-        const RptPerVertexData &a = vertices[tri[0]], &b = vertices[tri[1]], &cc = vertices[tri[2]];
-        float* o = shade.data() + 16 * (size_t)wi;
-        o[0] = a.normal[0]; o[1] = a.normal[1]; o[2] = a.normal[2]; o[3] = a.uv0[0];
-        o[4] = b.normal[0]; o[5] = b.normal[1]; o[6] = b.normal[2]; o[7] = a.uv0[1];
-        o[8] = cc.normal[0]; o[9] = cc.normal[1]; o[10] = cc.normal[2]; o[11] = b.uv0[0];
-        o[12] = b.uv0[1]; o[13] = cc.uv0[0]; o[14] = cc.uv0[1]; o[15] = 0.0f;
-        if (any_normal_map) {
-            float* tg = tangent.data() + 12 * (size_t)wi;
-            for (int k = 0; k < 3; ++k) { tg[k] = a.tangent[k]; tg[4 + k] = b.tangent[k]; tg[8 + k] = cc.tangent[k]; }
-            tg[3] = tg[7] = tg[11] = 0.0f;
+    // per-triangle shading records in wide order (three scattered vertex reads per triangle: shared out over the host threads)
+    UninitVector<float> shade, tangent;  // (every word is written by the loop below)
+    shade.resize((size_t)ntriangles * 16);
+    tangent.resize(any_normal_map ? (size_t)ntriangles * 12 : 0);
+    host_parallel_for(ntriangles, [&](uint32_t begin, uint32_t end) {
+        for (uint32_t wi = begin; wi < end; ++wi) {
+            const uint32_t* tri = triangles + 4 * (size_t)wide.orig_index[wi];
+            const RptPerVertexData &a = vertices[tri[0]], &b = vertices[tri[1]], &cc = vertices[tri[2]];
+            float* o = shade.data() + 16 * (size_t)wi;
+            o[0] = a.normal[0]; o[1] = a.normal[1]; o[2] = a.normal[2]; o[3] = a.uv0[0];
+            o[4] = b.normal[0]; o[5] = b.normal[1]; o[6] = b.normal[2]; o[7] = a.uv0[1];
+            o[8] = cc.normal[0]; o[9] = cc.normal[1]; o[10] = cc.normal[2]; o[11] = b.uv0[0];
+            o[12] = b.uv0[1]; o[13] = cc.uv0[0]; o[14] = cc.uv0[1]; o[15] = 0.0f;
+            if (any_normal_map) {
+                float* tg = tangent.data() + 12 * (size_t)wi;
+                for (int k = 0; k < 3; ++k) { tg[k] = a.tangent[k]; tg[4 + k] = b.tangent[k]; tg[8 + k] = cc.tangent[k]; }
+                tg[3] = tg[7] = tg[11] = 0.0f;
+            }
         }
-    }
+    });
 
     // light-pick table -> bins over compact light records (a one-entry table with ratio < 0 is the sentinel)
     std::vector<LightBin> bins;

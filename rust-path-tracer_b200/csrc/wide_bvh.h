@@ -23,6 +23,9 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
+#include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/rpt_shared_structs.h"
@@ -34,10 +37,20 @@ struct WideNode {
 };
 static_assert(sizeof(WideNode) == 80, "wide node is five 16-byte words");
 
+// std::vector whose resize() leaves new elements uninitialised: the big per-triangle arrays are written exactly once,
+// by the build threads, and a serial zero fill (plus its page faults) of ~60 bytes per triangle is start-up time.
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+    template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using UninitVector = std::vector<T, DefaultInitAllocator<T>>;
+
 struct WideBvh {
     std::vector<WideNode> nodes;
-    std::vector<float> tri_pos;        // 12 floats per triangle
-    std::vector<uint32_t> orig_index;  // wide order -> reference triangle index
+    UninitVector<float> tri_pos;        // 12 floats per triangle
+    UninitVector<uint32_t> orig_index;  // wide order -> reference triangle index
     std::vector<uint32_t> wide_index;  // reference triangle index -> wide order
     uint32_t max_depth = 0;            // levels below the root (stack entries needed <= max_depth + 1)
     uint32_t inner_children = 0, leaf_children = 0;

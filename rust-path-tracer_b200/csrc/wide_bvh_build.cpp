@@ -19,14 +19,19 @@
 namespace rpt {
 namespace {
 
+// fminf / fmaxf written out (the compiler calls libm for them otherwise)
+inline float min_f(float x, float y) { return x < y ? x : (x > y ? y : (y != y ? x : y)); }
+inline float max_f(float x, float y) { return x > y ? x : (x < y ? y : (y != y ? x : y)); }
+
+// (No default member initialisers: arrays of boxes are allocated for whole tree levels and filled by the build threads.)
 struct Box3 {
-    float lo[3] = {INFINITY, INFINITY, INFINITY};
-    float hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float lo[3], hi[3];
+    static Box3 empty() { return {{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}}; }
     void grow(const float* p) {
-        for (int k = 0; k < 3; ++k) { lo[k] = std::fmin(lo[k], p[k]); hi[k] = std::fmax(hi[k], p[k]); }
+        for (int k = 0; k < 3; ++k) { lo[k] = min_f(lo[k], p[k]); hi[k] = max_f(hi[k], p[k]); }
     }
     void grow(const Box3& b) {
-        for (int k = 0; k < 3; ++k) { lo[k] = std::fmin(lo[k], b.lo[k]); hi[k] = std::fmax(hi[k], b.hi[k]); }
+        for (int k = 0; k < 3; ++k) { lo[k] = min_f(lo[k], b.lo[k]); hi[k] = max_f(hi[k], b.hi[k]); }
     }
     double half_area() const {
         const double e[3] = {(double)hi[0] - lo[0], (double)hi[1] - lo[1], (double)hi[2] - lo[2]};
@@ -44,7 +49,7 @@ struct Item {
 // The (at most eight) children of one wide node while it is being assembled.
 struct Kids {
     Item v[8];
-    int n = 0;
+    int n;
     bool push(const Item& it) { if (n >= 8) return false; v[n++] = it; return true; }
 };
 
@@ -195,8 +200,8 @@ class Collapser {
     bool run(const char** error) {
         if (!plan_bottom_up()) { *error = "malformed BVH: child index out of range or node referenced twice"; return false; }
         out_.nodes.assign(1, WideNode{});
-        out_.tri_pos.assign((size_t)ntris_ * 12, 0.0f);
-        out_.orig_index.assign(ntris_, 0u);
+        out_.tri_pos.resize((size_t)ntris_ * 12);  // (left uninitialised: every record is written below, which the final check verifies)
+        out_.orig_index.resize(ntris_);
         out_.wide_index.assign(ntris_, 0xFFFFFFFFu);
 
         Item root;
@@ -210,21 +215,28 @@ class Collapser {
             bool ok;
         };
         std::vector<Pending> level{{root, 0u}}, next;
-        std::vector<Built> built;
+        std::unique_ptr<Built[]> built;  // (plain data, allocated uninitialised: 400 bytes per node of the widest level)
+        size_t built_capacity = 0;
         uint32_t emitted = 0;
         for (uint32_t depth = 0; !level.empty(); ++depth) {
             out_.max_depth = depth;
-            built.resize(level.size());
-            parallel_for(level.size(), [&](size_t i) { built[i].ok = choose_children(level[i].item, built[i].kids); });
+            if (level.size() > built_capacity) {
+                built_capacity = level.size() + level.size() / 2;
+                built.reset(new Built[built_capacity]);
+            }
+            parallel_for(level.size(), [&](size_t i) {
+                Built& b = built[i];
+                b.ok = choose_children(level[i].item, b.kids);
+                b.inner = b.triangles = 0;
+                for (int k = 0; b.ok && k < b.kids.n; ++k) {
+                    if (splittable(b.kids.v[k])) b.inner++;
+                    else b.triangles += b.kids.v[k].count;
+                }
+            });
             uint32_t node_cursor = (uint32_t)out_.nodes.size(), tri_cursor = emitted;
             for (size_t i = 0; i < level.size(); ++i) {
                 Built& b = built[i];
                 if (!b.ok) { *error = "malformed BVH: child index or triangle range out of bounds"; return false; }
-                b.inner = b.triangles = 0;
-                for (int k = 0; k < b.kids.n; ++k) {
-                    if (splittable(b.kids.v[k])) b.inner++;
-                    else b.triangles += b.kids.v[k].count;
-                }
                 b.child_base = node_cursor;
                 b.tri_base = tri_cursor;
                 node_cursor += b.inner;
@@ -239,7 +251,7 @@ class Collapser {
             parallel_for(level.size(), [&](size_t i) {
                 Built& b = built[i];
                 // ---- octant-ordered slots: slot s prefers the child lying farthest against direction ds(s)
-                b.box = Box3{};
+                b.box = Box3::empty();
                 for (int k = 0; k < b.kids.n; ++k) b.box.grow(b.kids.v[k].box);
                 int slot_of[8];
                 assign_slots(b.kids, b.box, slot_of, b.kid_in_slot);
@@ -347,7 +359,7 @@ class Collapser {
     }
     static bool splittable(const Item& it) { return !it.is_range || it.count > 3; }
     Box3 range_box(uint32_t first, uint32_t count) const {
-        Box3 b;
+        Box3 b = Box3::empty();
         for (uint32_t t = first; t < first + count; ++t)
             for (int k = 0; k < 3; ++k) b.grow(verts_[tris_[4 * (size_t)t + k]].vertex);
         return b;
