@@ -172,10 +172,12 @@ def test_parallel_bvh_build_is_identical_to_the_sequential_one(monkeypatch):
 
     scene = helpers.proxy_world.__wrapped__  # noqa: F841  (keep the cached world out of this: build from raw buffers)
     rs = np.random.default_rng(5)
-    nt = 40000
+    nt = 150000  # above the size from which several workers bin one node together
     centers = rs.random((nt, 3)).astype(np.float32) * np.float32(20.0)
     verts = np.zeros((nt * 3, 4), np.float32)
     verts[:, :3] = np.repeat(centers, 3, axis=0) + rs.normal(0, 0.05, (nt * 3, 3)).astype(np.float32)
+    zeros = rs.random(nt * 3) < 0.05  # exact ties, with both signs of zero, for the min / max merges
+    verts[zeros, 0] = np.where(rs.random(int(zeros.sum())) < 0.5, np.float32(0.0), np.float32(-0.0))
     tris0 = np.zeros((nt, 4), np.uint32)
     tris0[:, :3] = np.arange(nt * 3, dtype=np.uint32).reshape(nt, 3)
     results = []
@@ -188,3 +190,53 @@ def test_parallel_bvh_build_is_identical_to_the_sequential_one(monkeypatch):
                                             C.byref(n)), "rpt_build_bvh")
         results.append((nodes[: n.value].tobytes(), tris.tobytes()))
     assert all(r == results[0] for r in results[1:])
+
+
+def test_every_split_matches_numpy_restatement():
+    """Every node of a 400-triangle tree — from the dense root (more triangles than bins) down to the sparse nodes the
+    builder sweeps over filled bins only — against the independent float32 restatement of the reference's sweep."""
+    import ctypes as C
+
+    from rust_path_tracer_b200 import capi
+
+    rs = np.random.default_rng(11)
+    nt = 400
+    centers = (rs.random((nt, 3)) * [8.0, 3.0, 5.0]).astype(np.float32)
+    verts = np.zeros((nt * 3, 4), np.float32)
+    verts[:, :3] = np.repeat(centers, 3, axis=0) + rs.normal(0, 0.2, (nt * 3, 3)).astype(np.float32)
+    verts[::17, 1] = np.float32(1.5)  # repeated coordinates: equal centroids on one axis, empty bin runs
+    tris = np.zeros((nt, 4), np.uint32)
+    tris[:, :3] = np.arange(nt * 3, dtype=np.uint32).reshape(nt, 3)
+    nodes = np.zeros(2 * nt - 1, capi.BVH_NODE_DTYPE)
+    n = C.c_uint32(0)
+    capi.check(capi.lib().rpt_build_bvh(capi.ptr(verts), C.c_uint32(len(verts)), capi.ptr(tris), C.c_uint32(nt), C.c_uint32(128), capi.ptr(nodes),
+                                        C.byref(n)), "rpt_build_bvh")
+    nodes = nodes[: n.value]
+    pos = verts[:, :3]
+    v = pos[tris[:, :3]]
+    cent = ((v[:, 0] + v[:, 1]) + v[:, 2]) / np.float32(3.0)
+
+    def triangle_range(i):  # (first, count) of the subtree at node i
+        if nodes[i]["triangle_count"]:
+            return int(nodes[i]["left_or_first"]), int(nodes[i]["triangle_count"])
+        l = int(nodes[i]["left_or_first"])
+        (fl, cl), (fr, cr) = triangle_range(l), triangle_range(l + 1)
+        assert fl + cl == fr
+        return fl, cl + cr
+
+    f = np.float32
+    inner = leaves = 0
+    for i in range(len(nodes)):
+        first, count = triangle_range(i)
+        axis, plane, cost = numpy_best_split(pos, tris, cent, first, count)
+        e = (nodes[i]["aabb_max"] - nodes[i]["aabb_min"]).astype(f)
+        keep = f(f(f(e[0] * e[1]) + f(e[1] * e[2])) + f(e[2] * e[0])) * f(count)
+        left = int((cent[first:first + count, axis] < plane).sum())
+        if nodes[i]["triangle_count"] == 0:
+            inner += 1
+            assert not keep <= cost
+            assert triangle_range(int(nodes[i]["left_or_first"])) == (first, left), i
+        else:
+            leaves += 1
+            assert keep <= cost or left in (0, count), i
+    assert inner > 100 and leaves > 100
