@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -101,6 +102,13 @@ struct rpt_context {
     bool log_queues = false;  // RPT_LOG_QUEUES=1: print every bounce's queue lengths (syncs; for reading ncu captures)
     int trace_blocks_per_sm = 9;  // = the __launch_bounds__ of wf_trace_kernel: 56 registers, 36 warps per SM
     int refill_below = 20;
+    // Paths whose throughput is exactly zero are retired instead of traced to their first roulette (RPT_KEEP_DEAD_PATHS=1
+    // keeps them).  Exact whenever nothing such a path can still meet is non-finite — 0 x inf would be a NaN the
+    // reference adds to the pixel: sky texels and sun parameters are checked (sources_finite, frame_params); what is
+    // not covered is a dead path that later samples a NaN direction on degenerate geometry and escapes to an HDR sky,
+    // and the 2^-32 roulette draw of exactly 0 that would turn a dead path's throughput into NaN.
+    bool retire_dead_paths = true;
+    bool sources_finite = true;  // set by rpt_upload_world: sky texels finite, scene bounds finite and below 1e15
 
     // scene, reference layouts (megakernel arm)
     DevBuf<RptPerVertexData> d_vertices;
@@ -237,6 +245,8 @@ FrameParams frame_params(const rpt_context* c) {
     f.atlas = Atlas{c->d_atlas.p, c->atlas_w, c->atlas_h, pow2_mask(c->atlas_w), pow2_mask(c->atlas_h)};
     f.tile_rank = c->tile_rank;
     f.tile_count = c->tile_count;
+    f.retire_dead_paths = c->retire_dead_paths && c->sources_finite && std::isfinite(c->config.sun_direction[0]) && std::isfinite(c->config.sun_direction[1]) &&
+                          std::isfinite(c->config.sun_direction[2]) && std::isfinite(c->config.sun_direction[3]);
     return f;
 }
 
@@ -464,6 +474,7 @@ extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
     if (const char* v = getenv("RPT_REFILL_BELOW")) c->refill_below = atoi(v);
     if (const char* v = getenv("RPT_LOG_QUEUES")) c->log_queues = atoi(v) != 0;
     if (const char* v = getenv("RPT_GRAPHS")) c->use_graphs = atoi(v) != 0;
+    if (const char* v = getenv("RPT_KEEP_DEAD_PATHS")) c->retire_dead_paths = atoi(v) == 0;
     if (const char* v = getenv("RPT_WAVE_SLOTS")) c->wave_slots = (uint32_t)std::max(1024, atoi(v));
     *out_ctx = c;
     return RPT_OK;
@@ -645,7 +656,19 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
         c->atlas_w = c->atlas_h = 1;
     }
     const float magenta[16] = {1, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1};  // fallback_gpu_image, src/asset.rs:275-281
+    c->sources_finite = true;
+    for (int k = 0; k < 3; ++k) {  // (the binary root holds the scene bounds)
+        const float lo = nodes[0].aabb_min[k], hi = nodes[0].aabb_max[k];
+        if (!(std::fabs(lo) < 1e15f) || !(std::fabs(hi) < 1e15f)) c->sources_finite = false;
+    }
     if (sky_rgba32f) {
+        std::atomic<bool> finite{true};
+        host_parallel_for((uint32_t)std::min<uint64_t>((uint64_t)sky_w * sky_h, 0xFFFFFFFFull), [&](uint32_t begin, uint32_t end) {
+            bool ok = true;
+            for (size_t i = (size_t)begin * 4; i < (size_t)end * 4; ++i) ok &= std::isfinite(sky_rgba32f[i]);
+            if (!ok) finite.store(false, std::memory_order_relaxed);
+        });
+        if (!finite.load()) c->sources_finite = false;
         RPT_CUDA(c, c->d_sky.upload(reinterpret_cast<const float4*>(sky_rgba32f), (size_t)sky_w * sky_h, s));
         c->sky_w = sky_w; c->sky_h = sky_h;
     } else {

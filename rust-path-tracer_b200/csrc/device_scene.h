@@ -19,6 +19,7 @@ struct FrameParams {
     SkyImage sky;
     Atlas atlas;
     uint32_t tile_rank, tile_count;  // 32x32-tile round-robin partition (tile_count <= 1: whole frame)
+    uint32_t retire_dead_paths;      // a path whose throughput became exactly (0,0,0) is not continued (context.cu: when that is exact)
 };
 
 // ---- megakernel arm: reads the reference's own layouts ---------------------------------------

@@ -43,6 +43,16 @@ def render_oracle(world, cfg, seeds, spp, skybox=None):
     return out, rng, ids, ctr
 
 
+def check_ray_count(c_ctr, o_ctr, pipeline, tolerance):
+    """The megakernel arm traces what the reference traces; the wavefront pipeline retires paths whose throughput is
+    exactly zero (they cannot add anything), so it traces fewer rays — never more, and not implausibly fewer."""
+    ratio = c_ctr["nearest_rays"] / o_ctr["nearest_rays"]
+    if pipeline == capi.PIPELINE_MEGAKERNEL:
+        assert abs(ratio - 1) < tolerance
+    else:
+        assert 0.6 < ratio < 1 + tolerance
+
+
 CASES = [
     # scene, width, height, spp, nee
     ("FurnaceTest", 96, 96, 16, 0),
@@ -79,7 +89,7 @@ def test_matches_oracle(scene, w, h, spp, nee, pipeline):
     assert bad == int((~np.isfinite(o_out[:, :3]).all(axis=1)).sum()), "NaN pixels must match the CPU path's"
     assert err <= MAE_TOLERANCE, f"MAE {err}"
     assert c_ctr["paths"] == w * h * spp
-    assert c_ctr["nearest_rays"] == o_ctr["nearest_rays"] or abs(c_ctr["nearest_rays"] / o_ctr["nearest_rays"] - 1) < 2e-3
+    check_ray_count(c_ctr, o_ctr, pipeline, 2e-3)
 
 
 def test_wave_batching_is_invisible():
@@ -244,7 +254,7 @@ def test_russian_roulette_and_uniform_seeds():
         np.testing.assert_array_equal(c_rng, o_rng)
         np.testing.assert_array_equal(c_ids, o_ids)
         assert helpers.mae(c_out[:, :3] / 16, o_out[:, :3] / 16)[0] <= MAE_TOLERANCE
-        assert abs(c_ctr["nearest_rays"] / o_ctr["nearest_rays"] - 1) < 5e-3
+        check_ray_count(c_ctr, o_ctr, pipeline, 5e-3)
 
 
 def test_resume_from_previous_framebuffer():
@@ -322,7 +332,7 @@ def test_full_size_cornell_matches_oracle():
     assert mismatch <= ID_MISMATCH_BUDGET
     assert err <= MAE_TOLERANCE
     assert c_ctr["paths"] == 1024 * 1024 * spp
-    assert abs(c_ctr["nearest_rays"] / o_ctr["nearest_rays"] - 1) < 2e-3
+    check_ray_count(c_ctr, o_ctr, capi.PIPELINE_WAVEFRONT, 2e-3)
     assert c_ctr["any_rays"] <= o_ctr["any_rays"]  # shadow rays whose contribution is zero anyway are not traced
 
 
@@ -639,3 +649,24 @@ def test_create_destroy_cycles_do_not_leak():
     torch.cuda.synchronize()
     free_after, _ = torch.cuda.mem_get_info(0)
     assert free_before - free_after < 64 << 20, (free_before, free_after)  # (allocator caches aside, nothing accumulates)
+
+
+@pytest.mark.parametrize("scene,nee,sky", [("DarkCornell", 1, False), ("PBRTest", 0, False), ("VeachMIS", 1, False), ("PBRTest", 2, True)])
+def test_retiring_dead_paths_changes_nothing(scene, nee, sky, monkeypatch):
+    """Paths whose throughput is exactly (0, 0, 0) are retired instead of being traced to their first roulette bounce.
+    With RPT_KEEP_DEAD_PATHS=1 every ray of the reference is traced: the accumulator must be the same, bit for bit."""
+    world = helpers.world(scene)
+    w, h, spp = 192, 108, 16
+    cfg = helpers.config(w, h, nee, has_skybox=1 if sky else 0)
+    skybox = helpers.synthetic_sky() if sky else None
+    seeds = helpers.seeds(w, h)
+    o_ctr = render_oracle(world, cfg, seeds, spp, skybox)[3]
+    out, rng, _, ctr = render_cuda(world, cfg, seeds, spp, capi.PIPELINE_WAVEFRONT, skybox)
+    monkeypatch.setenv("RPT_KEEP_DEAD_PATHS", "1")
+    out_all, rng_all, _, ctr_all = render_cuda(world, cfg, seeds, spp, capi.PIPELINE_WAVEFRONT, skybox)
+    np.testing.assert_array_equal(out.view(np.uint32), out_all.view(np.uint32))
+    np.testing.assert_array_equal(rng, rng_all)
+    assert abs(ctr_all["nearest_rays"] / o_ctr["nearest_rays"] - 1) < 2e-3  # every ray of the reference
+    assert ctr["nearest_rays"] < ctr_all["nearest_rays"]
+    helpers.record_parity(f"{scene} nee={nee}{' HDR sky' if sky else ''}: retired dead paths", rays_traced_fraction=ctr["nearest_rays"] / ctr_all["nearest_rays"],
+                          accumulator_bits_changed=0)
