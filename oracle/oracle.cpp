@@ -565,6 +565,8 @@ V3 scatter(const float* sundir4, V3 origin, V3 direction) {  // skybox.rs:46-94
 }  // namespace sky
 
 // ------------------------------------------------------------------ kernels/src/lib.rs:21-186
+static bool g_retire_dead_paths = false;  // test switch, see oracle_set_retire_dead_paths
+
 struct PixelResult {
     V3 radiance;
     uint32_t primary_triangle;  // diagnostics: triangle_index of bounce 0, 0xFFFFFFFF on miss
@@ -669,6 +671,8 @@ PixelResult trace_pixel(uint32_t px, uint32_t py, const RptTracingConfig& cfg, u
             float prob = max_element(throughput);
             if (rng.r1() > prob) break;
             throughput = throughput * (1.0f / prob);
+        } else if (g_retire_dead_paths && is_zero(throughput)) {
+            break;  // NOT in the reference: see oracle_set_retire_dead_paths
         }
     }
     out.radiance = radiance;
@@ -688,6 +692,12 @@ std::vector<V4> to_float_texels(const uint8_t* rgba8, uint32_t w, uint32_t h) {
 
 // ====================================================================== C entry points (ctypes)
 extern "C" {
+
+// Checker for one optimisation of the CUDA backend (wavefront_shade.cu retires paths whose throughput is exactly zero):
+// with the switch on, the restatement stops such paths too, so tests can show on the CPU — at sizes and on scenes the
+// GPU tests do not cover — that the accumulator does not change in a single bit.  Off by default: the reference
+// walks those paths to their first roulette bounce.
+void oracle_set_retire_dead_paths(int on) { g_retire_dead_paths = on != 0; }
 
 struct OracleWorld {
     const RptPerVertexData* verts; uint32_t nverts;

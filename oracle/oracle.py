@@ -90,6 +90,11 @@ def trace(config, scene: OracleScene, seeds: np.ndarray, n_samples: int, output:
     return out, seeds, counters, ids
 
 
+def set_retire_dead_paths(on: bool):
+    """Test switch (off = the reference): stop paths whose throughput is exactly zero, like the CUDA backend does."""
+    lib().oracle_set_retire_dead_paths(C.c_int(int(on)))
+
+
 def intersect(scene: OracleScene, rays: np.ndarray, any_hit: bool = False, max_t: np.ndarray | None = None):
     rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
     n = len(rays)
