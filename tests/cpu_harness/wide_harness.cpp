@@ -179,4 +179,98 @@ int harness_wide_digest(const RptPerVertexData* verts, uint32_t nverts, const ui
     out[2] = (uint32_t)wide.nodes.size(); out[3] = wide.max_depth; out[4] = wide.inner_children; out[5] = wide.leaf_children;
     return 0;
 }
+// Experiment: a 32-lane warp of the extend kernel simulated on the CPU, to estimate warp-level
+// instruction counts of traversal policies before building them.  Lanes pull rays from a cursor and are refilled
+// when fewer than `refill_below` hold a ray (like wf_trace_kernel); one "node round" is charged whenever at least one
+// lane visits a node, one "triangle round" whenever at least one lane tests a triangle.
+//   defer_threshold == 0: the kernel as it is — every lane tests its triangles right after its visit.
+//   defer_threshold  > 0: a lane parks the triangle groups of its visits (`slots` of them) and keeps traversing; the
+//                         warp runs triangle rounds only when that many lanes have a parked group, when a lane has no
+//                         slot left for a new group, or when nothing else is left to do.  A lane whose traversal is
+//                         over waits for the next flush.
+// out: [0] node rounds, [1] lane-visits, [2] triangle rounds, [3] lane-tests, [4] rays, [5] refills,
+//      [6] rays whose result differs from the plain per-ray loop (must be 0: parking changes when, not what, is tested)
+int harness_warp_sim(const RptPerVertexData* verts, uint32_t nverts, const uint32_t* tris, uint32_t ntris, const RptBVHNode* nodes, uint32_t nnodes,
+                     const float* rays_o_d, uint32_t nrays, int refill_below, int defer_threshold, int slots, uint64_t* out) {
+    rpt::WideBvh wide;
+    const char* err = "";
+    if (!rpt::build_wide_bvh(nodes, nnodes, tris, ntris, verts, nverts, wide, &err)) return -1;
+    rpt::WideScene scene{reinterpret_cast<const rpt::uint4*>(wide.nodes.data()), reinterpret_cast<const rpt::float4*>(wide.tri_pos.data()), rpt::kHalf1024Bytes};
+    struct Group { rpt::uint2 tgroup; uint32_t tvalid; };
+    struct Lane {
+        rpt::WideCursor<true> c;
+        LocalStack st;
+        bool busy = false;
+        uint32_t ray = 0;
+        std::vector<Group> parked;  // triangle groups of earlier visits
+    };
+    std::vector<Lane> lanes(32);
+    uint64_t node_rounds = 0, lane_visits = 0, tri_rounds = 0, lane_tests = 0, refills = 0, wrong = 0;
+    uint32_t fetch = 0;
+    auto live = [&] { int n = 0; for (const Lane& l : lanes) n += l.busy; return n; };
+    auto flush = [&] {  // every lane tests one triangle per round until nothing is parked or pending
+        for (;;) {
+            int active = 0;
+            for (Lane& l : lanes) {
+                if (!l.busy) continue;
+                if (!l.c.has_triangles()) {
+                    if (l.parked.empty()) continue;
+                    l.c.tgroup = l.parked.back().tgroup;
+                    l.c.tvalid = l.parked.back().tvalid;
+                    l.parked.pop_back();
+                }
+                l.c.test_triangle(scene);
+                ++active;
+            }
+            if (!active) break;
+            ++tri_rounds;
+            lane_tests += (uint64_t)active;
+        }
+    };
+    for (;;) {
+        if (fetch < nrays && live() < refill_below) {
+            ++refills;
+            for (Lane& l : lanes) {
+                if (l.busy || fetch >= nrays) continue;
+                l.ray = fetch;
+                const float* r = rays_o_d + 6 * (size_t)fetch++;
+                l.c.begin(rpt::mk3(r[0], r[1], r[2]), rpt::mk3(r[3], r[4], r[5]), 0.0f);
+                l.st.clear();
+                l.parked.clear();
+                l.busy = true;
+            }
+        }
+        if (live() == 0) break;
+        // ---- node round
+        int visiting = 0;
+        bool slot_needed = false;
+        for (Lane& l : lanes) {
+            if (!l.busy || !l.c.has_nodes()) continue;
+            if (l.c.has_triangles()) {  // the group of the previous visit moves to a slot (there is one: see below)
+                l.parked.push_back(Group{l.c.tgroup, l.c.tvalid});
+                l.c.tgroup.y = 0u;
+            }
+            l.c.visit_node(scene, l.st);
+            ++visiting;
+            if (l.c.has_triangles() && (int)l.parked.size() >= slots) slot_needed = true;  // no slot for this group at the next visit
+        }
+        if (visiting) { ++node_rounds; lane_visits += (uint64_t)visiting; }
+        // ---- triangle rounds
+        int holding = 0;
+        for (const Lane& l : lanes) holding += l.busy && (l.c.has_triangles() || !l.parked.empty());
+        if (defer_threshold == 0 || slot_needed || holding >= defer_threshold || visiting == 0) flush();
+        for (Lane& l : lanes)
+            if (l.busy && !l.c.has_nodes() && !l.c.has_triangles() && l.parked.empty()) {
+                l.busy = false;
+                const float* r = rays_o_d + 6 * (size_t)l.ray;
+                LocalStack st;
+                const rpt::WideHit want = rpt::wide_intersect<true>(scene, rpt::mk3(r[0], r[1], r[2]), rpt::mk3(r[3], r[4], r[5]), 0.0f, st);
+                const rpt::WideHit got = l.c.result();
+                if (got.hit != want.hit || (got.hit && (got.triangle != want.triangle || std::memcmp(&got.t, &want.t, 4) != 0 || got.backface != want.backface))) ++wrong;
+            }
+    }
+    out[6] = wrong;
+    out[0] = node_rounds; out[1] = lane_visits; out[2] = tri_rounds; out[3] = lane_tests; out[4] = nrays; out[5] = refills;
+    return 0;
+}
 }
