@@ -18,6 +18,9 @@
 #include <cstdint>
 #include <cstring>
 #include <deque>
+#include <atomic>
+#include <thread>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/rpt_errors.h"
@@ -154,22 +157,35 @@ extern "C" int rpt_atlas_pack(const uint8_t* const* textures_rgba8, const uint32
     const int rc = rpt_atlas_rects(ntextures, atlas_w, atlas_h, rects.data());
     if (rc != RPT_OK) return rc;
     std::memset(atlas_rgba8_out, 0, (size_t)atlas_w * atlas_h * 4);  // DynamicImage::new_rgba8: transparent black
-    for (uint32_t i = 0; i < ntextures; ++i) {
+    for (uint32_t i = 0; i < ntextures; ++i)
         if (!textures_rgba8[i] || widths[i] == 0 || heights[i] == 0) return RPT_ERR_INVALID_ARGUMENT;
-        const uint32_t x = rects[4 * i], y = rects[4 * i + 1], w = rects[4 * i + 2], h = rects[4 * i + 3];
-        std::vector<uint8_t> resized;
-        const uint8_t* texels = textures_rgba8[i];
-        if (widths[i] != w || heights[i] != h) {
-            resized = resize_rgba8(texels, widths[i], heights[i], w, h);
-            texels = resized.data();
+    // Every texture owns its rectangle of the atlas: the resizes run on the host threads (RPT_BUILD_THREADS, like the
+    // BVH builders), textures handed out one at a time.
+    unsigned threads = std::max(1u, std::thread::hardware_concurrency());
+    if (const char* v = std::getenv("RPT_BUILD_THREADS")) threads = (unsigned)std::max(1, std::atoi(v));
+    threads = std::min<unsigned>(threads, std::max(1u, ntextures));
+    std::atomic<uint32_t> next{0};
+    auto worker = [&] {
+        for (uint32_t i; (i = next.fetch_add(1)) < ntextures;) {
+            const uint32_t x = rects[4 * i], y = rects[4 * i + 1], w = rects[4 * i + 2], h = rects[4 * i + 3];
+            std::vector<uint8_t> resized;
+            const uint8_t* texels = textures_rgba8[i];
+            if (widths[i] != w || heights[i] != h) {
+                resized = resize_rgba8(texels, widths[i], heights[i], w, h);
+                texels = resized.data();
+            }
+            for (uint32_t row = 0; row < h; ++row)  // flipv, then copy_from at (x, y)
+                std::memcpy(atlas_rgba8_out + ((size_t)(y + row) * atlas_w + x) * 4, texels + (size_t)(h - 1 - row) * w * 4, (size_t)w * 4);
+            sts_out[4 * i + 0] = (float)x / (float)atlas_w;
+            sts_out[4 * i + 1] = (float)y / (float)atlas_w;  // sic: the reference divides the y offset by the width
+            sts_out[4 * i + 2] = (float)w / (float)atlas_w;
+            sts_out[4 * i + 3] = (float)h / (float)atlas_h;
         }
-        for (uint32_t row = 0; row < h; ++row)  // flipv, then copy_from at (x, y)
-            std::memcpy(atlas_rgba8_out + ((size_t)(y + row) * atlas_w + x) * 4, texels + (size_t)(h - 1 - row) * w * 4, (size_t)w * 4);
-        sts_out[4 * i + 0] = (float)x / (float)atlas_w;
-        sts_out[4 * i + 1] = (float)y / (float)atlas_w;  // sic: the reference divides the y offset by the width
-        sts_out[4 * i + 2] = (float)w / (float)atlas_w;
-        sts_out[4 * i + 3] = (float)h / (float)atlas_h;
-    }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (std::thread& t : pool) t.join();
     return RPT_OK;
 }
 
