@@ -137,3 +137,72 @@ def test_collapse_rejects_malformed_trees(harness, monkeypatch):
         bad = world.nodes.copy()
         bad["left_or_first"][inner[-1]] = 0                     # a cycle through the root
         assert wide_digest(harness, world, bad)[0] == -1
+
+
+def _soup_world(verts_xyz, name):
+    """A World built by the product's own host builders (rpt_build_bvh etc.) from a bare triangle soup."""
+    from rust_path_tracer_b200.glb import BakedScene
+    from rust_path_tracer_b200.world import World
+
+    base = BakedScene.load(helpers.SCENE_DIR + "/DarkCornell.npz")
+    nt = len(verts_xyz) // 3
+    scene = BakedScene.__new__(BakedScene)
+    scene.__dict__.update(base.__dict__)
+    scene.vertices = np.concatenate([np.asarray(verts_xyz, np.float32), np.ones((nt * 3, 1), np.float32)], axis=1)
+    scene.normals = np.tile(np.array([[0, 1, 0, 0]], np.float32), (nt * 3, 1))[:, : base.normals.shape[1]]
+    scene.tangents = np.tile(np.array([[1, 0, 0, 0]], np.float32), (nt * 3, 1))[:, : base.tangents.shape[1]]
+    scene.uvs = np.zeros((nt * 3, base.uvs.shape[1]), np.float32)
+    idx = np.zeros((nt, 4), np.uint32)
+    idx[:, :3] = np.arange(nt * 3, dtype=np.uint32).reshape(nt, 3)
+    scene.indices = idx
+    scene.textures = [{} for _ in base.materials]
+    return World.from_baked(scene)
+
+
+DEGENERATE = ["coincident", "flat", "duplicates", "slivers", "one"]
+
+
+@pytest.mark.parametrize("kind", DEGENERATE)
+def test_degenerate_geometry_traces_like_the_reference(harness, kind):
+    """Geometry that stresses the builders' corner cases — all centroids equal (no axis can split: one over-full
+    leaf), everything in one plane, exact duplicates (exact-t ties), needle triangles, a single triangle — must still
+    trace exactly like the reference traversal of the same binary tree."""
+    rs = np.random.default_rng(23)
+    if kind == "coincident":  # 300 different triangles around one common centroid
+        a = rs.normal(size=(300, 3)); b = rs.normal(size=(300, 3))
+        v = np.stack([a, b, -(a + b)], axis=1).reshape(-1, 3) * 0.5 + [0.0, 1.0, 0.0]
+    elif kind == "flat":  # 2000 triangles in the plane y = 1
+        c = rs.random((2000, 1, 3)) * [4, 0, 4]
+        v = (c + rs.normal(0, 0.05, (2000, 3, 3)) * [1, 0, 1] + [-2.0, 1.0, -2.0]).reshape(-1, 3)
+    elif kind == "duplicates":  # every triangle four times
+        c = rs.random((250, 1, 3)) * 3
+        t = (c + rs.normal(0, 0.2, (250, 3, 3))) + [-1.5, 0.0, -1.5]
+        v = np.repeat(t, 4, axis=0).reshape(-1, 3)
+    elif kind == "slivers":  # needles spanning the whole scene
+        p = rs.random((400, 3)) * 4 - 2
+        q = rs.random((400, 3)) * 4 - 2
+        v = np.stack([p, q, p + rs.normal(0, 1e-4, (400, 3))], axis=1).reshape(-1, 3) + [0.0, 1.0, 0.0]
+    else:
+        v = np.array([[-1, 0, 0], [1, 0, 0], [0, 2, 0]], np.float64)
+    world = _soup_world(v.astype(np.float32), kind)
+    osc = om.OracleScene(world)
+    rays, max_t = make_rays(world, 20000, rs)
+    oh, ot, ott, ob = om.intersect(osc, rays)
+    wh, wt, wtt, wb, _ = wide_intersect(harness, world, rays)
+    np.testing.assert_array_equal(wh, oh)
+    both = oh == 1
+    tie = both & (wt != ot)  # (duplicates: any copy may win, at the same t)
+    if kind in ("flat", "duplicates"):
+        # Overlapping coplanar triangles: their t differ by rounding only, and the reference's own box test (tmin computed
+        # by a division, compared with a t from Moeller-Trumbore) can cull the node of the triangle that is an ulp
+        # nearer.  The wide tree's boxes are conservative, so it returns the true minimum: never farther, at most 2 ulp nearer.
+        ulps = ott[tie].view(np.int32).astype(np.int64) - wtt[tie].view(np.int32).astype(np.int64)
+        assert (ulps >= 0).all() and (ulps <= 2).all()
+    else:
+        assert (wtt[tie].view(np.uint32) == ott[tie].view(np.uint32)).all()
+        assert tie.mean() <= 1e-3
+    np.testing.assert_array_equal(wtt[both & ~tie].view(np.uint32), ott[both & ~tie].view(np.uint32))
+    oh, *_ = om.intersect(osc, rays, any_hit=True, max_t=max_t)
+    wh, *_ = wide_intersect(harness, world, rays, any_hit=True, max_t=max_t)
+    np.testing.assert_array_equal(wh, oh)
+    assert both.sum() > 20 or kind == "one"
