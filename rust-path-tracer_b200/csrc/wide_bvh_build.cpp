@@ -385,7 +385,7 @@ class Collapser {
             for (int i = 0; i < n; ++i) {
                 double c = 0.0;
                 for (int k = 0; k < 3; ++k) c += (0.5 * ((double)kids[i].box.lo[k] + kids[i].box.hi[k]) - nc[k]) * ds[k];
-                cost[s][i] = c;
+                cost[s][i] = std::isfinite(c) ? c : 0.0;  // (an empty box — triangles with NaN vertices only — has no centre)
             }
         }
         for (int s = 0; s < 8; ++s) kid_in_slot[s] = -1;
@@ -427,9 +427,11 @@ class Collapser {
         for (int k = 0; k < 3; ++k) {
             const double extent = (double)nb.hi[k] - (double)nb.lo[k];
             int ex = -126;
-            if (extent > 0.0) {
+            if (extent > 0.0 && extent < 1e37) {
                 ex = (int)std::ceil(std::log2(extent / 255.0));
                 while (std::ceil(extent / std::ldexp(1.0, ex)) > 255.0) ++ex;  // log2 rounding guard
+            } else if (extent > 0.0) {
+                ex = 127;  // (not reachable through build_wide_bvh, which rejects such coordinates)
             }
             ex = std::min(std::max(ex, -126), 127);
             e[k] = (uint8_t)(ex + 127);
@@ -487,8 +489,14 @@ bool build_wide_bvh(const RptBVHNode* nodes, uint32_t nnodes, const uint32_t* tr
     *error = none;
     if (!nodes || !triangles || !vertices || nnodes == 0 || ntriangles == 0) { *error = "empty scene"; return false; }
     for (size_t t = 0; t < (size_t)ntriangles; ++t)
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 3; ++k) {
             if (triangles[4 * t + k] >= nvertices) { *error = "triangle references a vertex out of range"; return false; }
+            // NaN coordinates are fine (min / max ignore them and such a triangle is never hit, as in the reference);
+            // infinite or astronomically large ones would overflow the quantised-box arithmetic into NaN and hide
+            // whole subtrees, so they are refused instead of traced wrongly.
+            const float* p = vertices[triangles[4 * t + k]].vertex;
+            if (std::fabs(p[0]) > 1e15f || std::fabs(p[1]) > 1e15f || std::fabs(p[2]) > 1e15f) { *error = "vertex coordinate infinite or beyond 1e15"; return false; }
+        }
     out = WideBvh{};
     Collapser c(nodes, nnodes, triangles, ntriangles, vertices, nvertices, out);
     c.threads_ = std::max(1u, std::thread::hardware_concurrency());

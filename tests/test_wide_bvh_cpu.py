@@ -5,6 +5,8 @@ import ctypes as C
 import os
 import subprocess
 
+import warnings
+
 import numpy as np
 import pytest
 
@@ -42,7 +44,9 @@ def wide_intersect(lib, world, rays, any_hit=False, max_t=None):
 
 def make_rays(world, n, rs):
     pos = world.per_vertex_buffer["vertex"][:, :3]
-    lo, hi = pos.min(0), pos.max(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        lo, hi = np.nanmin(pos, axis=0), np.nanmax(pos, axis=0)  # (some test scenes carry NaN vertices)
     c, ext = (lo + hi) / 2, (hi - lo).max()
     o = (c + (rs.random((n, 3)) - 0.5) * ext * 1.2).astype(np.float32)
     d = rs.normal(size=(n, 3))
@@ -159,7 +163,7 @@ def _soup_world(verts_xyz, name):
     return World.from_baked(scene)
 
 
-DEGENERATE = ["coincident", "flat", "duplicates", "slivers", "one"]
+DEGENERATE = ["coincident", "flat", "duplicates", "slivers", "one", "nan_vertices", "all_nan"]
 
 
 @pytest.mark.parametrize("kind", DEGENERATE)
@@ -182,6 +186,9 @@ def test_degenerate_geometry_traces_like_the_reference(harness, kind):
         p = rs.random((400, 3)) * 4 - 2
         q = rs.random((400, 3)) * 4 - 2
         v = np.stack([p, q, p + rs.normal(0, 1e-4, (400, 3))], axis=1).reshape(-1, 3) + [0.0, 1.0, 0.0]
+    elif kind in ("nan_vertices", "all_nan"):  # NaN coordinates: ignored by every min / max, such triangles are never hit
+        v = (rs.random((1500, 1, 3)) * 4 - 2 + rs.normal(0, 0.15, (1500, 3, 3))).reshape(-1, 3)
+        v[:: (1 if kind == "all_nan" else 1201)] = np.nan  # (all of them, or 4 scattered vertices: more would make the binary tree deeper than the reference's own stack)
     else:
         v = np.array([[-1, 0, 0], [1, 0, 0], [0, 2, 0]], np.float64)
     world = _soup_world(v.astype(np.float32), kind)
@@ -205,4 +212,21 @@ def test_degenerate_geometry_traces_like_the_reference(harness, kind):
     oh, *_ = om.intersect(osc, rays, any_hit=True, max_t=max_t)
     wh, *_ = wide_intersect(harness, world, rays, any_hit=True, max_t=max_t)
     np.testing.assert_array_equal(wh, oh)
-    assert both.sum() > 20 or kind == "one"
+    assert both.sum() > 20 or kind in ("one", "all_nan")
+    if kind == "all_nan":
+        assert both.sum() == 0
+
+
+def test_infinite_or_huge_coordinates_are_refused(harness):
+    """The quantised-box arithmetic would overflow into NaN and hide whole subtrees: refused at once (and not after
+    2^31 iterations of a rounding guard, which is what an infinite extent used to cost)."""
+    rs = np.random.default_rng(4)
+    base = (rs.random((500, 1, 3)) * 4 + rs.normal(0, 0.1, (500, 3, 3))).reshape(-1, 3).astype(np.float32)
+    for bad in (np.inf, -np.inf, 3e15, 1e30):
+        v = base.copy()
+        v[11, 1] = bad
+        world = _soup_world(v, "bad")
+        assert wide_digest(harness, world)[0] == -1
+    v = base.copy()
+    v[11, 1] = 9e14  # large but fine
+    assert wide_digest(harness, _soup_world(v, "large"))[0] == 0
