@@ -707,6 +707,9 @@ struct OracleWorld {
     const RptLightPickEntry* lights; uint32_t nlights;
     const uint8_t* atlas_rgba8; uint32_t atlas_w, atlas_h;   // may be NULL -> 1x1 white
     const float* sky_rgba32f; uint32_t sky_w, sky_h;         // may be NULL -> 2x2 magenta (src/asset.rs:283-290)
+    // The atlas as the CPU path reads it: float texels, converted ONCE before the sample loop (src/trace.rs:268-271).
+    // Optional: oracle_convert_atlas() output kept by the caller across oracle_trace calls; NULL -> converted per call.
+    const float* atlas_rgba32f;
 };
 
 struct OracleCounters {
@@ -723,6 +726,14 @@ int oracle_max_threads() {
 #endif
 }
 
+// RGBA8 -> the float texels of `dynamic_image_to_cpu_buffer` (src/asset.rs:266-273); out holds 4 * w * h floats.
+int oracle_convert_atlas(const uint8_t* rgba8, uint32_t w, uint32_t h, float* out) {
+    if (!rgba8 || !out) return -1;
+    const std::vector<V4> texels = to_float_texels(rgba8, w, h);
+    std::memcpy(out, texels.data(), texels.size() * sizeof(V4));
+    return 0;
+}
+
 // Advance every pixel by `n_samples` sample indices, exactly like n passes of the `while running`
 // body in trace_cpu (src/trace.rs:273-298): output[i] += (radiance, 1); rng[i] = (x + 1, y).
 // primary_ids (optional, width*height) receives the bounce-0 triangle_index of the LAST pass.
@@ -733,7 +744,9 @@ int oracle_trace(const RptTracingConfig* cfg, const OracleWorld* w, uint32_t* rn
     const V4 white = {1, 1, 1, 1};
     const V4 magenta[4] = {{1, 0, 1, 1}, {1, 0, 1, 1}, {1, 0, 1, 1}, {1, 0, 1, 1}};
     Scene s{w->verts, w->tris, w->nodes, w->mats, w->lights, w->nlights, {&white, 1, 1}, {magenta, 2, 2}};
-    if (w->atlas_rgba8) {
+    if (w->atlas_rgba8 && w->atlas_rgba32f) {
+        s.atlas = {reinterpret_cast<const V4*>(w->atlas_rgba32f), w->atlas_w, w->atlas_h};
+    } else if (w->atlas_rgba8) {
         atlas_f = to_float_texels(w->atlas_rgba8, w->atlas_w, w->atlas_h);
         s.atlas = {atlas_f.data(), w->atlas_w, w->atlas_h};
     }

@@ -23,6 +23,7 @@ class _World(C.Structure):
         ("nodes", C.c_void_p), ("nnodes", C.c_uint32), ("mats", C.c_void_p), ("nmats", C.c_uint32),
         ("lights", C.c_void_p), ("nlights", C.c_uint32), ("atlas", C.c_void_p), ("atlas_w", C.c_uint32),
         ("atlas_h", C.c_uint32), ("sky", C.c_void_p), ("sky_w", C.c_uint32), ("sky_h", C.c_uint32),
+        ("atlas_f32", C.c_void_p),
     ]
 
 
@@ -67,9 +68,15 @@ class OracleScene:
             None if skybox is None else np.ascontiguousarray(skybox, np.float32),
         ]
         v, t, n, m, l, a, s = self.keep
+        # the CPU path converts the atlas to float texels once, before its sample loop (src/trace.rs:268-271)
+        self.atlas_f32 = None
+        if a is not None:
+            self.atlas_f32 = np.empty(a.shape[:2] + (4,), np.float32)
+            if lib().oracle_convert_atlas(C.c_void_p(_ptr(a)), C.c_uint32(a.shape[1]), C.c_uint32(a.shape[0]), C.c_void_p(_ptr(self.atlas_f32))) != 0:
+                raise RuntimeError("oracle_convert_atlas failed")
         self.c = _World(_ptr(v), len(v), _ptr(t), len(t), _ptr(n), len(n), _ptr(m), len(m), _ptr(l), len(l),
                         _ptr(a), 0 if a is None else a.shape[1], 0 if a is None else a.shape[0],
-                        _ptr(s), 0 if s is None else s.shape[1], 0 if s is None else s.shape[0])
+                        _ptr(s), 0 if s is None else s.shape[1], 0 if s is None else s.shape[0], _ptr(self.atlas_f32))
 
 
 def trace(config, scene: OracleScene, seeds: np.ndarray, n_samples: int, output: np.ndarray | None = None, threads: int = 0,

@@ -8,7 +8,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-import weakref
 
 import numpy as np
 
@@ -117,12 +116,14 @@ def lib() -> C.CDLL:
 
 
 class _PinnedBlock:
-    """Owner of one rpt_host_alloc block; freed when the last numpy view of it is collected."""
+    """Owner of one rpt_host_alloc block.  It exposes the block through `__array_interface__`, so the numpy array made
+    from it — and, through numpy's base chain, every view, slice or reshape of that array — holds a reference to this
+    object; the page-locked memory is released when the last of them is collected."""
 
     def __init__(self, nbytes: int):
         self.address = C.c_void_p()
         check(lib().rpt_host_alloc(C.c_size_t(nbytes), C.byref(self.address)), "rpt_host_alloc")
-        self.buffer = (C.c_uint8 * nbytes).from_address(self.address.value)
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.address.value, False), "version": 3}
 
     def __del__(self):
         try:
@@ -133,18 +134,17 @@ class _PinnedBlock:
             pass
 
 
+def _array_over(owner, shape, dtype) -> np.ndarray:
+    """ndarray of `dtype` / `shape` over the bytes `owner` exposes; `owner` stays alive while any view of it does."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    return np.asarray(owner)[: count * dtype.itemsize].view(dtype).reshape(shape)
+
+
 def pinned_empty(shape, dtype) -> np.ndarray:
     """An uninitialised numpy array in page-locked host memory (rpt_host_alloc); needs a CUDA device."""
     dtype = np.dtype(dtype)
-    count = int(np.prod(shape))
-    block = _PinnedBlock(max(1, count * dtype.itemsize))
-    arr = np.frombuffer(block.buffer, dtype=dtype, count=count).reshape(shape)
-    _PINNED_OWNERS[arr.ctypes.data] = block  # numpy keeps `block.buffer` alive, not `block`; tie their lifetimes
-    weakref.finalize(arr, _PINNED_OWNERS.pop, arr.ctypes.data, None)
-    return arr
-
-
-_PINNED_OWNERS: dict = {}
+    return _array_over(_PinnedBlock(max(1, int(np.prod(shape)) * dtype.itemsize)), shape, dtype)
 
 
 def ptr(a: np.ndarray | None):

@@ -297,18 +297,32 @@ WaveState wave_state(rpt_context* c) {
     return s;
 }
 
+void release_wave(rpt_context* c) {
+    c->w_ray_o.release(); c->w_ray_d.release(); c->w_thr.release(); c->w_rad.release();
+    c->w_sh_o.release(); c->w_sh_d.release(); c->w_sh_c.release(); c->w_hit.release();
+    c->w_q0.release(); c->w_q1.release(); c->w_qhit.release(); c->w_qmiss.release(); c->w_qshaded.release(); c->w_qshadow.release();
+    c->wave_capacity = 0;
+}
+
 int ensure_wave(rpt_context* c, uint32_t slots) {
     if (slots <= c->wave_capacity) return RPT_OK;
     c->drop_graphs();  // the path-state buffers move
-    RPT_CUDA(c, c->w_ray_o.alloc(slots)); RPT_CUDA(c, c->w_ray_d.alloc(slots)); RPT_CUDA(c, c->w_thr.alloc(slots));
-    RPT_CUDA(c, c->w_rad.alloc(slots));
-    RPT_CUDA(c, c->w_sh_o.alloc(slots)); RPT_CUDA(c, c->w_sh_d.alloc(slots)); RPT_CUDA(c, c->w_sh_c.alloc(slots));
-    RPT_CUDA(c, c->w_hit.alloc(slots));
-    RPT_CUDA(c, c->w_q0.alloc(slots)); RPT_CUDA(c, c->w_q1.alloc(slots)); RPT_CUDA(c, c->w_qhit.alloc(slots)); RPT_CUDA(c, c->w_qmiss.alloc(slots));
-    RPT_CUDA(c, c->w_qshaded.alloc(slots)); RPT_CUDA(c, c->w_qshadow.alloc(slots));
-    if (!c->w_ctl.p) RPT_CUDA(c, c->w_ctl.alloc(1));
+    // All or nothing: a failed allocation leaves NO wave buffers (capacity 0), so the next call allocates again
+    // instead of launching on a half-resized set.
+    cudaError_t e = cudaSuccess;
+    auto grow = [&](auto& buf) { if (e == cudaSuccess) e = buf.alloc(slots); };
+    grow(c->w_ray_o); grow(c->w_ray_d); grow(c->w_thr); grow(c->w_rad);
+    grow(c->w_sh_o); grow(c->w_sh_d); grow(c->w_sh_c); grow(c->w_hit);
+    grow(c->w_q0); grow(c->w_q1); grow(c->w_qhit); grow(c->w_qmiss); grow(c->w_qshaded); grow(c->w_qshadow);
+    if (e == cudaSuccess && !c->w_ctl.p) e = c->w_ctl.alloc(1);
     // (only for trees deeper than the shared-memory part of the traversal stack)
-    if (c->deep_tree && !c->w_stack_overflow.p) RPT_CUDA(c, c->w_stack_overflow.alloc(trace_stack_overflow_entries(c->sm_count * c->trace_blocks_per_sm)));
+    if (e == cudaSuccess && c->deep_tree && !c->w_stack_overflow.p)
+        e = c->w_stack_overflow.alloc(trace_stack_overflow_entries(c->sm_count * c->trace_blocks_per_sm));
+    if (e != cudaSuccess) {
+        release_wave(c);
+        cudaGetLastError();
+        return c->fail(RPT_ERR_CUDA, "path-state allocation for %u slots: %s", slots, cudaGetErrorString(e));
+    }
     c->wave_capacity = slots;
     return RPT_OK;
 }
@@ -546,10 +560,9 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     for (size_t t = 0; t < (size_t)ntriangles; ++t)
         if (triangles[4 * t + 3] >= nmaterials) return c->fail(RPT_ERR_INVALID_ARGUMENT, "triangle %zu references material %u of %u", t, triangles[4 * t + 3], nmaterials);
     RPT_TRY(bind_device(c));
-    c->has_world = false;
-    c->drop_graphs();
 
-    // ---- private re-layout (host side, once per scene)
+    // ---- private re-layout (host side, once per scene).  Nothing of the context is touched until the input has
+    // been validated and every host-side layout built: a rejected scene leaves the previous world in place.
     WideBvh wide;
     const char* err = "";
     if (!build_wide_bvh(nodes, nnodes, triangles, ntriangles, vertices, nvertices, wide, &err)) return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: %s", err);
@@ -628,7 +641,9 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
         if (records.size() >= (1u << 23)) return c->fail(RPT_ERR_UNSUPPORTED, "more than 2^23 emissive triangles (the path state keeps the sampled light in 23 bits)");
     }
 
-    // ---- uploads
+    // ---- uploads (from here on the previous world is gone, whatever happens)
+    c->has_world = false;
+    c->drop_graphs();
     cudaStream_t s = c->stream;
     RPT_CUDA(c, c->d_vertices.upload(vertices, nvertices, s));
     RPT_CUDA(c, c->d_triangles.upload(reinterpret_cast<const uint4*>(triangles), ntriangles, s));
@@ -794,10 +809,26 @@ extern "C" int rpt_host_free(void* ptr) {
 extern "C" int rpt_enqueue(rpt_context* c, uint32_t n_samples) {
     RPT_TRY(check_ready(c));
     if (n_samples == 0) return RPT_OK;
+    // Device time of every batch (rpt_get_device_ms).  Pairs whose batch has completed are folded into the running
+    // total here, so a host that never asks — an interactive session of millions of batches — holds a handful of events.
+    while (c->timed.size() > 8 && cudaEventQuery(c->timed.front().second) == cudaSuccess) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, c->timed.front().first, c->timed.front().second) == cudaSuccess) c->device_ms += t;
+        cudaEventDestroy(c->timed.front().first);
+        cudaEventDestroy(c->timed.front().second);
+        c->timed.erase(c->timed.begin());
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     RPT_CUDA(c, cudaEventCreate(&e0));
-    RPT_CUDA(c, cudaEventCreate(&e1));
-    RPT_CUDA(c, cudaEventRecord(e0, c->stream));
+    if (const cudaError_t e = cudaEventCreate(&e1); e != cudaSuccess) {
+        cudaEventDestroy(e0);
+        return c->cuda(e, "cudaEventCreate");
+    }
+    if (const cudaError_t e = cudaEventRecord(e0, c->stream); e != cudaSuccess) {
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return c->cuda(e, "cudaEventRecord");
+    }
     int status = RPT_OK;
     if (c->pipeline == RPT_PIPELINE_MEGAKERNEL) {
         c->launch(RPT_STAGE_MEGAKERNEL, [&] { launch_mega_trace(mega_params(c), n_samples, c->stream); });
@@ -807,7 +838,12 @@ extern "C" int rpt_enqueue(rpt_context* c, uint32_t n_samples) {
     } else {
         status = for_each_wave(c, n_samples, [&](const WaveDesc& d) { return run_wave_graphed(c, d); });
     }
-    cudaEventRecord(e1, c->stream);
+    const cudaError_t rec = cudaEventRecord(e1, c->stream);
+    if (rec != cudaSuccess) {
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return status != RPT_OK ? status : c->cuda(rec, "cudaEventRecord");
+    }
     c->timed.emplace_back(e0, e1);
     return status;
 }

@@ -80,12 +80,14 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
                 s.rad[slot] = r;
                 alive = false;
             } else if (f.nee == RPT_NEE_MIS) {  // calculate_bsdf_mis_contribution, light_pick.rs:179-199
+                // (with the "no lights" sentinel table the reference's default DirectLightSample has area 0, i.e.
+                // light pdf 0: the term is 0 and the path ends — there is no light record to read)
                 // The reference multiplies the throughput BEFORE the last bounce by that bounce's spectrum / pdf; that
                 // product is the current throughput times the Russian-roulette probability it was divided by
                 // (o4.w; 1 when no roulette ran), so no per-path copy of either factor is kept.
-                const LightRecord& L = w.lights[flags >> 9];
                 f3 c = splat3(0.0f);
-                if (tri == __float_as_uint(__ldg(&L.e2_tri).w)) {
+                const LightRecord& L = w.lights[w.nbins > 0u ? flags >> 9 : 0u];
+                if (w.nbins > 0u && tri == __float_as_uint(__ldg(&L.e2_tri).w)) {
                     const float4 la = __ldg(&L.a_area);
                     const float lp = light_pdf(la.w, t, xyz(__ldg(&L.normal)), rd);
                     if (lp > 0.0f) {

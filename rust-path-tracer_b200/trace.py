@@ -7,10 +7,10 @@ Same names and meaning as the Rust API so tests and benches read like the refere
     trace_gpu("tests/golden/scenes/FurnaceTest.npz", None, state)   # src/trace.rs:136-224
     state.framebuffer                                    # packed RGB f32, output.xyz / samples
 
-`trace_gpu` keeps the reference loop's structure — batches of `sync_rate` samples, `samples`
-advanced per batch, readback + normalisation per batch, flush on `interacting | dirty` — but each
-batch is ONE `rpt_enqueue(sync_rate)` (the device loops over the samples) instead of
-`sync_rate` x (dispatch + poll).  There is no `trace_cpu` here: the CPU path of the reference is
+`trace_gpu` keeps the reference loop's structure — batches of `sync_rate` samples (ONE sample while
+`interacting | dirty`, like the reference's early exit from its dispatch loop), `samples` advanced
+per batch, readback + normalisation per batch, flush on `interacting | dirty` — but each batch is
+ONE `rpt_enqueue(n)` (the device loops over the samples) instead of n x (dispatch + poll).  There is no `trace_cpu` here: the CPU path of the reference is
 the oracle (oracle/), which is test infrastructure, not product.
 
 `Renderer` is the thin object over the C ABI (include/rpt_b200.h) that `trace_gpu`, the tests
@@ -270,8 +270,9 @@ def trace_gpu(scene_path: str, skybox_path: str | None, state: TracingState, dev
             r.write_output(init * np.float32(state.samples))
 
         while state.running:
-            finished = state.sync_rate
+            # the reference leaves its dispatch loop after ONE sample while the camera moves (src/trace.rs:187-193)
             flush = state.interacting or state.dirty
+            finished = 1 if flush else state.sync_rate
             r.enqueue(finished)
             r.sync()
             state.samples += finished
@@ -281,6 +282,16 @@ def trace_gpu(scene_path: str, skybox_path: str | None, state: TracingState, dev
             if flush:  # src/trace.rs:216-222
                 state.dirty = False
                 state.samples = 0
+                if (state.config.width, state.config.height) != (width, height):
+                    # The reference sizes every buffer once, before the loop, and would index out of bounds after a
+                    # resize; here a resized config gets fresh seeds and a fresh framebuffer.
+                    width, height = state.config.width, state.config.height
+                    fresh = make_rng_seeds(width, height, use_blue_noise=state.use_blue_noise)
+                    seeds = capi.pinned_empty(fresh.shape, np.uint32)
+                    seeds[...] = fresh
+                    with state.lock:
+                        state.framebuffer = capi.pinned_empty(width * height * 3, np.float32)
+                        state.framebuffer[...] = 0.0
                 r.set_config(state.config)
                 r.write_output(None)
                 r.write_rng(seeds)

@@ -1,0 +1,220 @@
+"""Known answers for the tracing path that do NOT come from the oracle.
+
+The reference holds one golden value for this path (tests/correctness_tests.rs:14-33: FurnaceTest, pixel
+(65, 75), 0.8 +- 0.02 in gamma space), and that pixel only sees the diffuse lobe of an untextured grey sphere.
+Everything here widens the pins with answers derived from the reference's own formulas by closed form or by
+numpy quadrature, or from laws the reference's estimators obey by construction (an emitter seen from inside is a
+constant environment; a constant texture is a constant; NEE / MIS / Russian roulette are unbiased when the
+throughput stays below 1).  Each case is a (world, config, sky) triple plus a prediction, rendered by whoever
+calls it: the CPU oracle (tests/test_known_answers.py, CPU suite) and the CUDA path (same file, -m gpu).
+
+Scene: FurnaceTest.glb's fixture — a grey unit icosphere (material 0: albedo 0.18, roughness 1, metallic 0) at
+the origin inside an emissive shell of radius 6.85 (material 1: emission 3.0), camera (0, 1, -5) looking +z.
+"""
+from __future__ import annotations
+
+import functools
+import os
+
+import numpy as np
+
+import helpers
+
+SPHERE_CENTRE = np.zeros(3)
+SPHERE_RADIUS = 1.0
+SHELL_EMISSION = 3.0
+
+
+def _furnace_baked():
+    from rust_path_tracer_b200.glb import BakedScene
+
+    return BakedScene.load(os.path.join(helpers.SCENE_DIR, "FurnaceTest.npz"))
+
+
+def _clone(scene, indices=None, materials=None, textures=None):
+    from rust_path_tracer_b200.glb import BakedScene
+
+    return BakedScene(scene.vertices, scene.normals, scene.tangents, scene.uvs, scene.indices.copy() if indices is None else indices,
+                      scene.materials.copy() if materials is None else materials, textures if textures is not None else [dict() for _ in scene.materials])
+
+
+@functools.lru_cache(maxsize=None)
+def sphere_only_world(albedo=(0.18, 0.18, 0.18), roughness=1.0, metallic=0.0):
+    """The grey sphere without the shell (for constant-environment cases)."""
+    from rust_path_tracer_b200.world import World
+
+    base = _furnace_baked()
+    mats = base.materials.copy()
+    mats[0]["albedo"] = (*albedo, 1.0)
+    mats[0]["roughness"] = roughness
+    mats[0]["metallic"] = metallic
+    return World.from_baked(_clone(base, indices=base.indices[base.indices[:, 3] == 0].copy(), materials=mats))
+
+
+@functools.lru_cache(maxsize=None)
+def furnace_world(shell_albedo=None):
+    """The full furnace; shell_albedo = 0 makes the emitter reflect nothing in the diffuse lobe (NEE mode 2 shades
+    emitters hit after a diffuse bounce as ordinary surfaces, lib.rs:97-109)."""
+    from rust_path_tracer_b200.world import World
+
+    base = _furnace_baked()
+    mats = base.materials.copy()
+    if shell_albedo is not None:
+        mats[1]["albedo"] = (shell_albedo, shell_albedo, shell_albedo, 1.0)
+    return World.from_baked(_clone(base, materials=mats))
+
+
+@functools.lru_cache(maxsize=None)
+def constant_texture_furnace_world(byte=118):
+    """The furnace with the sphere's albedo / roughness / metallic coming from CONSTANT textures through the atlas,
+    packed by the product's atlas packer (albedo texels are gamma-decoded in 8 bits on the way, src/asset.rs:140-147:
+    118 -> 46, i.e. 0.1804).  Returns (world, equivalent untextured world)."""
+    from rust_path_tracer_b200.atlas import decode_albedo_gamma, pack_scene_textures
+    from rust_path_tracer_b200.world import World
+
+    base = _furnace_baked()
+    tex = [dict() for _ in base.materials]
+
+    def const(v):
+        img = np.empty((16, 16, 4), np.uint8)
+        img[..., :3] = v
+        img[..., 3] = 255
+        return img
+
+    tex[0] = {"albedo": const(byte), "roughness": const(255), "metallic": const(0)}
+    textured = _clone(base, textures=tex)
+    # keep the lookups strictly inside each rect: the CPU polyfill reads the texel at ceil(coord) too, which at uv = 1
+    # belongs to the neighbouring rect (image_polyfill.rs:38-46 — faithful bleeding, but not a constant any more)
+    textured.uvs = (0.25 + 0.5 * (base.uvs - np.floor(base.uvs))).astype(np.float32)
+    atlas = pack_scene_textures(textured, 256, 256)
+    w_tex = World.from_baked(textured, atlas=atlas)
+    mats = base.materials.copy()
+    a = np.float32(decode_albedo_gamma(const(byte))[0, 0, 0]) / np.float32(255.0)
+    mats[0]["albedo"] = (a, a, a, 1.0)
+    w_ref = World.from_baked(_clone(base, materials=mats))
+    return w_tex, w_ref
+
+
+def constant_sky(value=SHELL_EMISSION, width=8, height=4):
+    img = np.empty((height, width, 4), np.float32)
+    img[..., :3] = value
+    img[..., 3] = 1.0
+    return img
+
+
+# ---- analytic side ---------------------------------------------------------------------------------------------
+def sphere_pixel_cosines(width, height, cam=(0.0, 1.0, -5.0), margin=0.9):
+    """For pixel centres of the default camera (lib.rs:38-51, rotation 0): cos(angle between the view direction and
+    the sphere normal) where the primary ray hits the unit sphere inside `margin` of its silhouette radius, else NaN."""
+    ys, xs = np.mgrid[0:height, 0:width]
+    u = ((xs + 0.5) / width) * 2 - 1
+    v = (1 - (ys + 0.5) / height) * 2 - 1
+    v = v * (height / width)
+    d = np.stack([u, v, np.ones_like(u)], -1)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    o = np.asarray(cam, np.float64) - SPHERE_CENTRE
+    b = d @ o
+    c = o @ o - SPHERE_RADIUS ** 2
+    disc = b * b - c
+    hit = disc > 0
+    t = -b - np.sqrt(np.where(hit, disc, 0))
+    p = o + d * t[..., None]
+    n = p / SPHERE_RADIUS
+    cosv = -(n * d).sum(-1)
+    # impact parameter of the ray relative to the sphere radius: stay away from the silhouette, where the
+    # tessellated sphere and its interpolated normals differ from the ideal one
+    impact = np.sqrt(np.maximum(o @ o - b * b, 0)) / SPHERE_RADIUS
+    return np.where(hit & (impact < margin), cosv, np.nan)
+
+
+def schlick(cos_theta, f0):
+    return f0 + (1 - f0) * (1 - cos_theta) ** 5
+
+
+@functools.lru_cache(maxsize=None)
+def _diffuse_table(f0=0.04, n_table=256, n_theta=400, n_phi=400):
+    """E over cosine-distributed directions d of 1 - Schlick(h . v), h = normalize(v + d), as a function of
+    cos(theta_v): the expected diffuse-lobe weight of `PBR::sample` per unit albedo when the lobe is always chosen
+    (bsdf.rs:202-211, 301-315: kd = (1 - ks)(1 - metallic); spectrum / pdf = kd * albedo / (1 - specular_weight))."""
+    cv = np.linspace(0.0, 1.0, n_table)
+    # midpoint rule in (r1, phi): cosine-weighted sampling has cos^2(theta) = r1 uniformly distributed
+    r1 = (np.arange(n_theta) + 0.5) / n_theta
+    phi = (np.arange(n_phi) + 0.5) / n_phi * 2 * np.pi
+    ct = np.sqrt(r1)[:, None]
+    st = np.sqrt(1 - r1)[:, None]
+    dx, dy, dz = st * np.cos(phi)[None, :], st * np.sin(phi)[None, :], ct * np.ones_like(phi)[None, :]
+    out = np.empty(n_table)
+    for i, c in enumerate(cv):
+        vx, vz = np.sqrt(max(0.0, 1 - c * c)), c
+        hx, hy, hz = dx + vx, dy, dz + vz
+        hv = (hx * vx + hz * vz) / np.sqrt(hx * hx + hy * hy + hz * hz)
+        out[i] = (1 - schlick(np.maximum(hv, 0.0), f0)).mean()
+    return cv, out
+
+
+def diffuse_only_prediction(width, height, albedo, environment):
+    """Image of the sphere under a constant environment when only the diffuse lobe exists (specular_weight_clamp =
+    (0, 0)); NaN outside the sphere's interior."""
+    cosv = sphere_pixel_cosines(width, height)
+    cv, table = _diffuse_table()
+    e = np.interp(np.nan_to_num(cosv, nan=1.0), cv, table)
+    img = environment * np.asarray(albedo, np.float64)[None, None, :] * e[..., None]
+    img[np.isnan(cosv)] = np.nan
+    return img
+
+
+def mirror_prediction(width, height, albedo, metallic, environment):
+    """Roughness -> 0 and specular_weight_clamp = (1, 1): `sample_ggx` returns the mirror direction, D cancels
+    between spectrum and pdf, the Schlick-GGX geometry term is 1, so spectrum / pdf = Schlick(n . v, f0) with
+    f0 = lerp(0.04, albedo, metallic) (bsdf.rs:212-233, 316-334; util.rs:58-85, 211-236)."""
+    cosv = sphere_pixel_cosines(width, height)
+    f0 = 0.04 + (np.asarray(albedo, np.float64) - 0.04) * metallic
+    img = environment * schlick(np.nan_to_num(cosv, nan=1.0)[..., None], f0[None, None, :])
+    img[np.isnan(cosv)] = np.nan
+    return img
+
+
+def relative_error_of_mean(image, prediction):
+    """|mean(image) / mean(prediction) - 1| per channel over the pixels the prediction covers."""
+    mask = np.isfinite(prediction).all(-1)
+    return np.abs(image[mask].mean(0) / prediction[mask].mean(0) - 1.0), int(mask.sum())
+
+
+def gradient_sky(width=256, height=128):
+    """A smooth lat-long image whose bilinear interpolation is (almost) exact: texel = linear in u and v."""
+    v, u = np.mgrid[0:height, 0:width]
+    img = np.empty((height, width, 4), np.float32)
+    img[..., 0] = u / width
+    img[..., 1] = v / height
+    img[..., 2] = 0.25
+    img[..., 3] = 1.0
+    return img
+
+
+def sky_lookup_prediction(width, height, sky, sun_direction, cam_rotation=(0.0, 0.0)):
+    """numpy (float64) restatement of lib.rs:70-78 + image_polyfill.rs:32-55 for pixel-centre primary rays that
+    miss everything: yaw by atan2(sun.z, sun.x), lat-long (u, v), bilinear with floor / ceil and wrap, x sun.w / 15."""
+    ys, xs = np.mgrid[0:height, 0:width]
+    u = ((xs + 0.5) / width) * 2 - 1
+    v = ((1 - (ys + 0.5) / height) * 2 - 1) * (height / width)
+    d = np.stack([u, v, np.ones_like(u)], -1)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    rx, ry = cam_rotation
+    cx, sx, cy, sy = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry)
+    rot_x = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    rot_y = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    d = d @ (rot_y @ rot_x).T
+    yaw = np.arctan2(sun_direction[2], sun_direction[0])
+    c, s = np.cos(yaw), np.sin(yaw)
+    r = d @ np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]]).T
+    su = 0.5 + np.arctan2(r[..., 2], r[..., 0]) / (2 * np.pi)
+    sv = 1 - (0.5 + np.arcsin(np.clip(r[..., 1], -1, 1)) / np.pi)
+    h, w = sky.shape[:2]
+    px, py = su * w, sv * h
+    fx, fy = px - np.floor(px), py - np.floor(py)
+    x0, x1 = np.floor(px).astype(int) % w, np.ceil(px).astype(int) % w
+    y0, y1 = np.floor(py).astype(int) % h, np.ceil(py).astype(int) % h
+    s64 = sky.astype(np.float64)[..., :3]
+    top = s64[y0, x0] + (s64[y0, x1] - s64[y0, x0]) * fx[..., None]
+    bot = s64[y1, x0] + (s64[y1, x1] - s64[y1, x0]) * fx[..., None]
+    return (top + (bot - top) * fy[..., None]) * (sun_direction[3] / 15.0)

@@ -69,3 +69,30 @@ def test_null_arguments_are_status_codes():
     assert lib.rpt_destroy(None) == capi.ERR_INVALID_ARGUMENT
     assert lib.rpt_enqueue(None, C.c_uint32(1)) == capi.ERR_INVALID_ARGUMENT
     assert lib.rpt_build_bvh(None, 0, None, 0, 128, None, None) == capi.ERR_INVALID_ARGUMENT
+
+
+def test_staging_block_outlives_the_array_it_was_made_for():
+    """`pinned_empty` hands out views of a block whose owner must live as long as ANY view does (a reshaped
+    framebuffer outliving the original array was freed under it once).  Checked on the lifetime logic itself with a
+    malloc-free stand-in for the page-locked block, so it runs without a GPU."""
+    import gc
+
+    freed = []
+
+    class Block:
+        def __init__(self, nbytes):
+            self.store = np.zeros(nbytes, np.uint8)
+            self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.store.ctypes.data, False), "version": 3}
+
+        def __del__(self):
+            freed.append(True)
+
+    arr = capi._array_over(Block(4 * 6), (2, 3), np.float32)
+    view = arr.reshape(3, 2)[1:]
+    del arr
+    gc.collect()
+    assert not freed, "block released while a view of it is alive"
+    view[...] = 1.0
+    del view
+    gc.collect()
+    assert freed

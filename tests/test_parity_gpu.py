@@ -670,3 +670,79 @@ def test_retiring_dead_paths_changes_nothing(scene, nee, sky, monkeypatch):
     assert ctr["nearest_rays"] < ctr_all["nearest_rays"]
     helpers.record_parity(f"{scene} nee={nee}{' HDR sky' if sky else ''}: retired dead paths", rays_traced_fraction=ctr["nearest_rays"] / ctr_all["nearest_rays"],
                           accumulator_bits_changed=0)
+
+
+# ---- the benchmarked workloads at the sizes they are benchmarked at -----------------------------------------------
+# bench.py's inputs come from bench.load_workload, so these tests see exactly what the bench line is measured on.
+
+def _full_size_case(workload, spp, label, mae_tolerance=MAE_TOLERANCE):
+    import bench
+
+    world, cfg, seeds, _spp, _label, _scene, sky = bench.load_workload(workload)
+    o_out, o_rng, o_ids, o_ctr = render_oracle(world, cfg, seeds, spp, sky)
+    c_out, c_rng, c_ids, c_ctr = render_cuda(world, cfg, seeds, spp, capi.PIPELINE_WAVEFRONT, sky)
+    np.testing.assert_array_equal(c_rng, o_rng)
+    mismatch = float((c_ids != o_ids).mean())
+    err, bad = helpers.mae(c_out[:, :3] / spp, o_out[:, :3] / spp)
+    nan_cuda = int((~np.isfinite(c_out[:, :3]).all(axis=1)).sum())
+    nan_oracle = int((~np.isfinite(o_out[:, :3]).all(axis=1)).sum())
+    helpers.record_parity(label, id_mismatch=mismatch, mae=err, nan_pixels_cuda=nan_cuda, nan_pixels_oracle=nan_oracle,
+                          triangles=int(world.ntriangles), width=int(cfg.width), height=int(cfg.height), spp=spp)
+    assert mismatch <= ID_MISMATCH_BUDGET
+    assert err <= mae_tolerance
+    assert nan_cuda == nan_oracle
+    assert c_ctr["paths"] == cfg.width * cfg.height * spp
+    check_ray_count(c_ctr, o_ctr, capi.PIPELINE_WAVEFRONT, 2e-3)
+    return c_out, o_out
+
+
+def test_bench_workload_breaktime_proxy_at_full_size():
+    """The default bench workload as benchmarked: ~1M-triangle BreakTime proxy, 1920x1080, 4096^2 atlas, 2048x1024
+    HDR sky, MIS — 2 samples of every pixel against the oracle (ids, MAE, NaN count, rng state, ray counts)."""
+    _full_size_case("breaktime", 2, "BreakTime proxy 1M tris 1920x1080 2spp MIS (bench workload, full size)")
+
+
+def test_config2_pbrtest_at_full_size():
+    """configs[2]: PBRTest 1920x1080, procedural sky (every path ends in `scatter`), 2 of its 512 samples."""
+    _full_size_case("pbr", 2, "PBRTest 1920x1080 2spp procedural sky (configs[2] frame)")
+
+
+def test_config2_textured_pbrtest_at_full_size():
+    """configs[2] with the synthetic 4096^2 metallic / roughness / albedo / normal atlas."""
+    _full_size_case("pbr-textured", 2, "PBRTest+textures 1920x1080 2spp 4096^2 atlas (configs[2] frame)")
+
+
+def test_config3_veachmis_radiance_at_full_size():
+    """configs[3]: VeachMIS 1920x1080 with MIS, radiance (not only ids) of 2 samples."""
+    _full_size_case("veach", 2, "VeachMIS 1920x1080 2spp MIS radiance (configs[3] frame)")
+
+
+def test_config4_4k_tile_union_matches_oracle():
+    """configs[4]: the 3840x2160 frame of the BreakTime proxy rendered as EIGHT tile partitions (what eight GPUs
+    would each render) on one GPU; the union of the partitions against 1 sample of the oracle."""
+    import bench
+
+    world, cfg, seeds, _spp, _label, _scene, sky = bench.load_workload("breaktime-4k")
+    o_out, o_rng, o_ids, _ = render_oracle(world, cfg, seeds, 1, sky)
+    union = np.zeros_like(o_out)
+    with Renderer(0) as r:
+        r.upload_world(world, sky)
+        r.set_config(cfg)
+        r.write_rng(seeds)
+        ids = r.read_primary_ids()
+        owners = np.zeros(len(o_out), np.int32)
+        for rank in range(8):
+            r.set_tile_partition(rank, 8)
+            r.write_rng(seeds)
+            r.write_output(None)
+            r.enqueue(1)
+            part = r.read_output()
+            owners += (part[:, 3] > 0).astype(np.int32)
+            union += part
+    assert (owners == 1).all()  # every pixel belongs to exactly one partition
+    mismatch = float((ids != o_ids).mean())
+    err, bad = helpers.mae(union[:, :3], o_out[:, :3])
+    helpers.record_parity("BreakTime proxy 3840x2160 1spp, union of 8 tile partitions (configs[4] frame)", id_mismatch=mismatch, mae=err, nan_pixels=bad)
+    assert mismatch <= ID_MISMATCH_BUDGET
+    assert err <= MAE_TOLERANCE
+    assert (union[:, 3] == 1.0).all()
