@@ -52,7 +52,7 @@ WORKLOADS = {
     # synthetic inputs (rust-path-tracer_b200/scenes.py): the shipped assets have no textures, and
     # scenes/BreakTime.glb is absent from the reference checkout (.MISSING_LARGE_BLOBS)
     "pbr-textured": ("PBRTest+procedural textures", 1920, 1080, 0, 16, "configs[2] PBRTest.glb 1920x1080 with a synthetic 4096^2 metallic/roughness/albedo/normal atlas"),
-    "breaktime": ("BreakTime PROXY (synthetic ~1M-triangle textured interior, HDR sky)", 1920, 1080, 1, 16,
+    "breaktime": ("BreakTime PROXY (synthetic ~1M-triangle textured interior, HDR sky)", 1920, 1080, 1, 64,
                   "north-star scene BreakTime.glb 1920x1080 — asset absent, LABELLED SYNTHETIC PROXY"),
     "breaktime-4k": ("BreakTime PROXY (synthetic ~1M-triangle textured interior, HDR sky)", 3840, 2160, 1, 4,
                      "configs[4] BreakTime.glb 3840x2160, HDR sky — asset absent, LABELLED SYNTHETIC PROXY (use --partition tiles)"),
@@ -175,50 +175,80 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def oracle_sample(world, cfg, seeds, spp, threads=0, sky=None):
-    """Time the CPU oracle on `spp` samples of the workload; returns (seconds, counters, threads used)."""
-    threads = threads or host_threads()
-    sys.path.insert(0, os.path.join(REPO, "oracle"))
-    import oracle as oracle_mod
+class OracleRunner:
+    """The CPU oracle on one workload.  The scene object is built once — the CPU path converts the atlas to float
+    texels once, before its sample loop (src/trace.rs:268-271), and so does this."""
 
-    scene = oracle_mod.OracleScene(world, sky)
-    t0 = time.perf_counter()
-    _, _, ctr, _ = oracle_mod.trace(cfg, scene, seeds, spp, threads=threads)
-    return time.perf_counter() - t0, ctr, threads
+    def __init__(self, world, sky=None, threads=0):
+        sys.path.insert(0, os.path.join(REPO, "oracle"))
+        import oracle as oracle_mod
+
+        self.mod = oracle_mod
+        self.scene = oracle_mod.OracleScene(world, sky)
+        self.threads = threads or host_threads()
+
+    def sample(self, cfg, seeds, spp, want_primary_ids=False):
+        """Returns (seconds, counters, output running sum, primary ids or None)."""
+        t0 = time.perf_counter()
+        out, _, ctr, ids = self.mod.trace(cfg, self.scene, seeds, spp, threads=self.threads, want_primary_ids=want_primary_ids)
+        return time.perf_counter() - t0, ctr, out, ids
+
+
+def workload_config(cfg, label, scene, spp, pipeline, world_size, tiles, wave_slots):
+    """The `config` object of the JSON line — the same for the GPU arm and the reference arm."""
+    npix = cfg.width * cfg.height
+    return {"workload": label, "scene": scene, "width": cfg.width, "height": cfg.height,
+            "nee": cfg.nee, "min_bounces": cfg.min_bounces, "max_bounces": cfg.max_bounces, "spp_per_step": spp,
+            "pipeline": pipeline,
+            "partition": (f"32x32 tiles round-robin x{world_size}, owned tiles gathered on rank 0" if tiles else f"sample-index range x{world_size} + ncclReduce") if world_size > 1 else "single GPU",
+            "l2": "working set per step (path state %.0f MB) exceeds the 126 MB L2" % (PATH_STATE_BYTES_PER_SLOT * min(npix * spp, wave_slots or (1 << 24)) / 1e6)}
+
+
+PATH_STATE_BYTES_PER_SLOT = 144.0
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The Rust crate cannot be
     built in this image (no Rust toolchain), so this arm times the oracle port — the C++ restatement
-    of trace_cpu + kernels::trace_pixel — with all host threads; each step is a bounded sample
-    (1 spp of the frame) of the same workload."""
+    of trace_cpu + kernels::trace_pixel — with all host threads, on the GPU arm's config.  Each step is a
+    BOUNDED SAMPLE of that config's step: `REFERENCE_SPP` sample indices of every pixel of the frame instead of
+    `spp_per_step` (Mpaths/s does not depend on the sample count; the scene and its float atlas are set up once,
+    outside the timed region, as in trace_cpu)."""
     rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    world, cfg, seeds, _spp, label, scene, sky = load_workload(args.workload)
-    ref_spp = 1
+    world, cfg, seeds, spp, label, scene, sky = load_workload(args.workload)
+    if args.spp:
+        spp = args.spp
+    ref_spp = min(REFERENCE_SPP, spp)
+    runner = OracleRunner(world, sky)
     for _ in range(args.warmup):
-        oracle_sample(world, cfg, seeds, ref_spp, sky=sky)
+        runner.sample(cfg, seeds, 1)
     times, rays = [], 0
-    for _ in range(args.steps):
-        dt, ctr, threads = oracle_sample(world, cfg, seeds, ref_spp, sky=sky)
+    for k in range(args.steps):
+        step_seeds = seeds.copy()
+        step_seeds[:, 0] += np.uint32(k * ref_spp)
+        dt, ctr, _, _ = runner.sample(cfg, step_seeds, ref_spp)
         times.append(dt)
         rays += ctr["nearest_rays"] + ctr["any_rays"]
     total = sum(times)
     paths = cfg.width * cfg.height * ref_spp * args.steps
     value = paths / total / 1e6
+    sample = f"{ref_spp} of the step's {spp} sample indices for every pixel of the {cfg.width}x{cfg.height} frame, per step; OpenMP rows (warm-up steps: 1 sample index)"
     line = {
         "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": label, "scene": scene, "width": cfg.width, "height": cfg.height,
-                   "nee": cfg.nee, "spp_per_step": ref_spp},
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong" if args.partition == "tiles" and world_size > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, label, scene, spp, args.pipeline, world_size, args.partition == "tiles" and world_size > 1, args.wave_slots),
         "mrays_per_s": rays / total / 1e6,
-        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": threads, "kind": "port",
-                         "sample": f"{ref_spp} spp of the full {cfg.width}x{cfg.height} frame per step, OpenMP rows"},
+        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": runner.threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+REFERENCE_SPP = 4  # sample indices per reference-arm step (about 7 s on 16 cores for the default workload)
 
 
 def run_b200(args):
@@ -303,11 +333,7 @@ def run_b200(args):
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * job_s / args.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": label, "scene": scene, "width": cfg.width, "height": cfg.height,
-                   "nee": cfg.nee, "min_bounces": cfg.min_bounces, "max_bounces": cfg.max_bounces, "spp_per_step": spp,
-                   "pipeline": args.pipeline,
-                   "partition": (f"32x32 tiles round-robin x{world_size} + ncclReduce" if tiles else f"sample-index range x{world_size} + ncclReduce") if world_size > 1 else "single GPU",
-                   "l2": "working set per step (path state %.0f MB) exceeds the 126 MB L2" % (144.0 * min(npix * spp, args.wave_slots or (1 << 24)) / 1e6)},
+        "config": workload_config(cfg, label, scene, spp, args.pipeline, world_size, tiles, args.wave_slots),
         "mrays_per_s": total_rays / job_s / 1e6,
         "wall_ms_per_step": 1e3 * wall_s / args.steps,
         "gpu_launches": ctr["kernel_launches"],
@@ -325,7 +351,9 @@ def run_b200(args):
         ext_ms, ext_launches = stages["extend"] if pipeline == capi.PIPELINE_WAVEFRONT else stages["megakernel"]
         # algorithmic bytes per nearest ray, in the reference's layout: 32 B per box slab-tested + 64 B per
         # triangle tested (16 B index + 3 x 16 B positions) — SURVEY.md §8(d); counted by the oracle on 1 spp
-        dt1, octr, threads = oracle_sample(world, cfg, seeds0, 1, sky=sky)
+        runner = OracleRunner(world, sky)
+        threads = runner.threads
+        dt1, octr, o_out, o_ids = runner.sample(cfg, seeds0, 1, want_primary_ids=True)
         boxes_n = octr["boxes_tested"] - octr["boxes_tested_any"]
         tris_n = octr["tris_tested"] - octr["tris_tested_any"]
         bytes_per_ray = (32.0 * boxes_n + 64.0 * tris_n) / max(octr["nearest_rays"], 1)
@@ -345,6 +373,22 @@ def run_b200(args):
             "stage_ms": {k: v[0] for k, v in stages.items() if v[1]},
             "note": "scene is L2-resident: algorithmic bytes are served by L1/L2, so frac can exceed DRAM traffic; see DESIGN.md",
         }
+    if rank == 0 and not args.quick and not tiles:
+        # ---- parity of THIS frame: sample index 0 of every pixel, GPU against the oracle run just made ----------
+        r.write_rng(seeds0)
+        r.write_output(None)
+        g_ids = r.read_primary_ids()
+        r.enqueue(1)
+        g_out = r.read_output()
+        ok = np.isfinite(g_out[:, :3]).all(axis=1) & np.isfinite(o_out[:, :3]).all(axis=1)
+        line["parity"] = {
+            "against": "CPU oracle (oracle/oracle.cpp), same scene, config, seeds; sample index 0 of every pixel",
+            "primary_id_mismatch_fraction": float((g_ids != o_ids).mean()), "primary_id_budget": 1e-4,
+            "mae": float(np.abs(g_out[ok, :3].astype(np.float64) - o_out[ok, :3]).mean()), "mae_tolerance": 1e-3,
+            "nan_pixels_gpu": int((~np.isfinite(g_out[:, :3]).all(axis=1)).sum()), "nan_pixels_oracle": int((~np.isfinite(o_out[:, :3]).all(axis=1)).sum()),
+            "pixels": int(npix), "spp": 1,
+        }
+        r.write_rng(seeds)
     if rank == 0 and not args.quick and pipeline == capi.PIPELINE_WAVEFRONT:
         tr = extend_traffic(args.workload)
         if tr:  # dram__bytes_read.sum + dram__bytes_write.sum of the profiled launch, scaled to this launch's ray count
@@ -355,7 +399,7 @@ def run_b200(args):
     if rank == 0 and not args.quick and dist is None:
         # ---- CPU baseline (N = 1 only): the oracle port on the host cores, bounded sample -----
         cpu_spp = max(1, min(8, int(15.0 / max(dt1, 1e-3))))
-        dtc, cctr, threads = oracle_sample(world, cfg, seeds0, cpu_spp, sky=sky)
+        dtc, cctr, _, _ = runner.sample(cfg, seeds0, cpu_spp)
         line["cpu_baseline"] = {"value": npix * cpu_spp / dtc / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "port",
                                 "mrays_per_s": (cctr["nearest_rays"] + cctr["any_rays"]) / dtc / 1e6,
                                 "sample": f"{cpu_spp} spp of the full {cfg.width}x{cfg.height} frame ({dtc:.1f} s), OpenMP rows"}
