@@ -102,6 +102,9 @@ struct rpt_context {
     bool log_queues = false;  // RPT_LOG_QUEUES=1: print every bounce's queue lengths (syncs; for reading ncu captures)
     int trace_blocks_per_sm = 9;  // = the __launch_bounds__ of wf_trace_kernel: 56 registers, 36 warps per SM
     int refill_below = 20;
+    // deferred triangle tests (wf_trace_deferred_kernel): RPT_DEFER_EXTEND / RPT_DEFER_SHADOW / RPT_FLUSH_AT / RPT_FLUSH_KEEP
+    bool defer_extend = false, defer_shadow = false;  // measured: -2 % extend time on the 1M-triangle proxy, +3.5 % on DarkCornell — off
+    int flush_at = 12, flush_keep = 6;
     // Paths whose throughput is exactly zero are retired instead of traced to their first roulette (RPT_KEEP_DEAD_PATHS=1
     // keeps them).  Exact whenever nothing such a path can still meet is non-finite — 0 x inf would be a NaN the
     // reference adds to the pixel: sky texels and sun parameters are checked (sources_finite, frame_params); what is
@@ -121,7 +124,8 @@ struct rpt_context {
     uint32_t atlas_w = 1, atlas_h = 1, sky_w = 2, sky_h = 2, nlights = 0, nmaterials = 0;
     // scene, private layouts (wavefront arm)
     DevBuf<uint4> d_wide_nodes;
-    DevBuf<float4> d_tri_pos, d_tri_shade, d_tri_tangent;
+    DevBuf<float4> d_tri_pos, d_tri_shade;
+    uint32_t shade_stride = kShadeStridePlain;
     DevBuf<LightBin> d_light_bins;
     DevBuf<LightRecord> d_light_records;
     uint32_t nbins = 0;
@@ -276,12 +280,13 @@ WideWorld wide_world(const rpt_context* c) {
     WideWorld w{};
     w.bvh = WideScene{c->d_wide_nodes.p, c->d_tri_pos.p, kHalf1024Bytes};
     w.tri_shade = c->d_tri_shade.p;
-    w.tri_tangent = c->d_tri_tangent.p;
+    w.shade_stride = c->shade_stride;
     w.materials = c->d_materials.p;
     w.nmaterials = c->nmaterials;
     w.light_bins = c->d_light_bins.p;
     w.nbins = c->nbins;
     w.lights = c->d_light_records.p;
+    w.nlights = (uint32_t)c->d_light_records.n;
     return w;
 }
 
@@ -364,7 +369,8 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
     const FrameParams f = frame_params(c);
     const WideWorld w = wide_world(c);
     const WaveState s = wave_state(c);
-    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below, c->deep_tree ? c->w_stack_overflow.p : nullptr};
+    const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below, c->deep_tree ? c->w_stack_overflow.p : nullptr,
+                       c->defer_extend, c->defer_shadow, c->flush_at, std::max(1, c->flush_keep)};
     const uint32_t nslots = d.npix * d.k_samples;
     c->launch(RPT_STAGE_OTHER, [&] { launch_wf_reset(l, s, 1, true); });
     c->launch(RPT_STAGE_GENERATE, [&] { launch_wf_generate(l, f, s, d, c->d_rng.p); });
@@ -487,6 +493,10 @@ extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
     if (const char* v = getenv("RPT_TRACE_BLOCKS_PER_SM")) c->trace_blocks_per_sm = std::max(1, atoi(v));
     if (const char* v = getenv("RPT_REFILL_BELOW")) c->refill_below = atoi(v);
     if (const char* v = getenv("RPT_LOG_QUEUES")) c->log_queues = atoi(v) != 0;
+    if (const char* v = getenv("RPT_DEFER_EXTEND")) c->defer_extend = atoi(v) != 0;
+    if (const char* v = getenv("RPT_DEFER_SHADOW")) c->defer_shadow = atoi(v) != 0;
+    if (const char* v = getenv("RPT_FLUSH_AT")) c->flush_at = atoi(v);
+    if (const char* v = getenv("RPT_FLUSH_KEEP")) c->flush_keep = atoi(v);
     if (const char* v = getenv("RPT_GRAPHS")) c->use_graphs = atoi(v) != 0;
     if (const char* v = getenv("RPT_KEEP_DEAD_PATHS")) c->retire_dead_paths = atoi(v) == 0;
     if (const char* v = getenv("RPT_WAVE_SLOTS")) c->wave_slots = (uint32_t)std::max(1024, atoi(v));
@@ -503,7 +513,7 @@ extern "C" int rpt_destroy(rpt_context* c) {
     for (auto& ev : c->timed) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     c->drain_stage_events();
     for (auto* b : {&c->w_ray_o, &c->w_ray_d, &c->w_thr, &c->w_rad, &c->w_sh_o, &c->w_sh_d, &c->w_sh_c, &c->d_tri_pos,
-                    &c->d_tri_shade, &c->d_tri_tangent, &c->d_sky, &c->d_output})
+                    &c->d_tri_shade, &c->d_sky, &c->d_output})
         b->release();
     c->w_hit.release(); c->w_stack_overflow.release(); c->w_q0.release(); c->w_q1.release(); c->w_qhit.release(); c->w_qmiss.release(); c->w_qshaded.release();
     c->w_qshadow.release(); c->w_ctl.release();
@@ -578,23 +588,30 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     }();
     if (textured && !atlas_rgba8) return c->fail(RPT_ERR_INVALID_ARGUMENT, "a material is textured but no atlas was supplied");
 
-    // per-triangle shading records in wide order (three scattered vertex reads per triangle: shared out over the host threads)
-    UninitVector<float> shade, tangent;  // (every word is written by the loop below)
-    shade.resize((size_t)ntriangles * 16);
-    tangent.resize(any_normal_map ? (size_t)ntriangles * 12 : 0);
+    // per-triangle shading records in wide order (layout: device_scene.h; three scattered vertex reads per triangle,
+    // shared out over the host threads).  a / e1 / e2 are copied from the traversal stream, so shading sees the bits
+    // the ray/triangle test saw.
+    const uint32_t shade_stride = any_normal_map ? kShadeStrideTangents : kShadeStridePlain;
+    UninitVector<float> shade;
+    shade.resize((size_t)ntriangles * shade_stride * 4);
     host_parallel_for(ntriangles, [&](uint32_t begin, uint32_t end) {
         for (uint32_t wi = begin; wi < end; ++wi) {
             const uint32_t* tri = triangles + 4 * (size_t)wide.orig_index[wi];
             const RptPerVertexData &a = vertices[tri[0]], &b = vertices[tri[1]], &cc = vertices[tri[2]];
-            float* o = shade.data() + 16 * (size_t)wi;
-            o[0] = a.normal[0]; o[1] = a.normal[1]; o[2] = a.normal[2]; o[3] = a.uv0[0];
-            o[4] = b.normal[0]; o[5] = b.normal[1]; o[6] = b.normal[2]; o[7] = a.uv0[1];
-            o[8] = cc.normal[0]; o[9] = cc.normal[1]; o[10] = cc.normal[2]; o[11] = b.uv0[0];
-            o[12] = b.uv0[1]; o[13] = cc.uv0[0]; o[14] = cc.uv0[1]; o[15] = 0.0f;
+            const float* pos = wide.tri_pos.data() + 12 * (size_t)wi;
+            float* o = shade.data() + (size_t)shade_stride * 4 * wi;
+            o[0] = pos[0]; o[1] = pos[1]; o[2] = pos[2]; o[3] = pos[7];  // a, bits(material)
+            o[4] = pos[4]; o[5] = pos[5]; o[6] = pos[6]; o[7] = a.uv0[0];
+            o[8] = pos[8]; o[9] = pos[9]; o[10] = pos[10]; o[11] = a.uv0[1];
+            o[12] = a.normal[0]; o[13] = a.normal[1]; o[14] = a.normal[2]; o[15] = b.uv0[0];
+            o[16] = b.normal[0]; o[17] = b.normal[1]; o[18] = b.normal[2]; o[19] = b.uv0[1];
+            o[20] = cc.normal[0]; o[21] = cc.normal[1]; o[22] = cc.normal[2]; o[23] = cc.uv0[0];
+            o[24] = cc.uv0[1];
             if (any_normal_map) {
-                float* tg = tangent.data() + 12 * (size_t)wi;
-                for (int k = 0; k < 3; ++k) { tg[k] = a.tangent[k]; tg[4 + k] = b.tangent[k]; tg[8 + k] = cc.tangent[k]; }
-                tg[3] = tg[7] = tg[11] = 0.0f;
+                for (int k = 0; k < 3; ++k) { o[25 + k] = a.tangent[k]; o[28 + k] = b.tangent[k]; o[31 + k] = cc.tangent[k]; }
+                for (int k = 34; k < 40; ++k) o[k] = 0.0f;
+            } else {
+                for (int k = 25; k < 32; ++k) o[k] = 0.0f;
             }
         }
     });
@@ -652,9 +669,8 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     RPT_CUDA(c, c->d_lights.upload(lights, nlights, s));
     RPT_CUDA(c, c->d_wide_nodes.upload(reinterpret_cast<const uint4*>(wide.nodes.data()), wide.nodes.size() * 5, s));
     RPT_CUDA(c, c->d_tri_pos.upload(reinterpret_cast<const float4*>(wide.tri_pos.data()), (size_t)ntriangles * 3, s));
-    RPT_CUDA(c, c->d_tri_shade.upload(reinterpret_cast<const float4*>(shade.data()), (size_t)ntriangles * 4, s));
-    if (any_normal_map) RPT_CUDA(c, c->d_tri_tangent.upload(reinterpret_cast<const float4*>(tangent.data()), (size_t)ntriangles * 3, s));
-    else c->d_tri_tangent.release();
+    RPT_CUDA(c, c->d_tri_shade.upload(reinterpret_cast<const float4*>(shade.data()), (size_t)ntriangles * shade_stride, s));
+    c->shade_stride = shade_stride;
     c->d_light_bins.release();
     c->d_light_records.release();
     if (!bins.empty()) {

@@ -266,17 +266,25 @@ struct WideCursor {
         }
     }
     // Tests the next pending triangle; returns true when an any-hit query is decided.
-    RPT_D bool test_triangle(const WideScene& s) {
+    RPT_D bool test_triangle(const WideScene& s) { return test_next<false>(s); }
+    template <bool ORDER_FREE>
+    RPT_D bool test_next(const WideScene& s) {
         const int k = highest_bit(tgroup.y);
         tgroup.y &= ~(1u << k);
-        const uint32_t ti = tgroup.x + (uint32_t)popcount(tvalid & ~(0xFFFFFFFFu << k));
+        return test_one<ORDER_FREE>(s, tgroup.x + (uint32_t)popcount(tvalid & ~(0xFFFFFFFFu << k)));
+    }
+    // Tests triangle `ti` (wide order); returns true when an any-hit query is decided.
+    // ORDER_FREE: among hits with bit-equal t the smallest wide index wins, so the result does not depend on the order
+    // in which a ray's candidate triangles are tested (deferred tests; the in-order loop keeps "first found wins").
+    template <bool ORDER_FREE>
+    RPT_D bool test_one(const WideScene& s, uint32_t ti) {
         const float4* rec = s.tri_pos + 3u * (size_t)ti;
         const float4 a = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
         float t;
         bool back;
         // accept 0.001 < t < best so far (nearest) resp. t <= max_t and t < 1e6 (any), intersection.rs:195
         if (ray_triangle(ray.o, ray.d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t, back) && t > 0.001f &&
-            (NEAREST ? t < best_t : (t <= best_t && t < 1000000.0f))) {
+            (NEAREST ? (t < best_t || (ORDER_FREE && t == best_t && hit_tri != kNoNode && ti < (hit_tri & 0x7FFFFFFFu))) : (t <= best_t && t < 1000000.0f))) {
             hit_t = t;
             hit_tri = ti | (back ? 0x80000000u : 0u);
             if (!NEAREST) return true;

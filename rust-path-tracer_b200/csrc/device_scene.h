@@ -64,14 +64,23 @@ struct LightBin {
 
 struct WideWorld {
     WideScene bvh;                     // nodes + triangle position stream
-    const float4* tri_shade;           // 4 per triangle
-    const float4* tri_tangent;         // 3 per triangle, or null when no material is normal-mapped
+    // One shading record per triangle, wide order, `shade_stride` float4 apart: everything wf_shade_kernel gathers for
+    // a hit in ONE aligned run of 32-byte sectors (it used to be three gathers from three streams):
+    //   [0] a.xyz, bits(material)   [1] e1.xyz, uv_a.x   [2] e2.xyz, uv_a.y
+    //   [3] n_a.xyz, uv_b.x         [4] n_b.xyz, uv_b.y  [5] n_c.xyz, uv_c.x    [6] uv_c.y, -, -, -       (7 float4, stride 8:
+    //   one 128-byte line) and, when a material is normal-mapped, the tangents in words [6].yzw [7] [8].xy (stride 10: five sectors).
+    const float4* tri_shade;
+    uint32_t shade_stride;             // 8 or 10 (kShadeStrideTangents: records carry tangents)
     const RptMaterialData* materials;
     uint32_t nmaterials;
     const LightBin* light_bins;        // null / nbins == 0: the "no lights" sentinel
     uint32_t nbins;
     const LightRecord* lights;
+    uint32_t nlights;                  // light records
 };
+
+constexpr uint32_t kShadeStridePlain = 8, kShadeStrideTangents = 10;
+constexpr uint32_t kSmemLightBytes = 4 * 1024;  // light records + bins are staged in shared memory when they fit this
 
 struct WaveCtl {
     uint32_t n_ext[2];  // rays queued for the current / next extend pass
@@ -113,6 +122,8 @@ struct WaveLaunch {
     int trace_blocks_per_sm;  // resident 128-thread blocks per SM of the trace kernels
     int refill_below;         // refill idle lanes once fewer than this many lanes of a warp hold a ray
     uint2* stack_overflow;    // global overflow area of the traversal stacks (trace_stack_overflow_entries); null when the tree fits the shared slab
+    bool defer_extend, defer_shadow;  // trace with deferred triangle tests (wf_trace_deferred_kernel)
+    int flush_at, flush_keep;         // triangle rounds start at / go on while this many lanes hold a queued triangle
 };
 
 size_t trace_stack_overflow_entries(int grid_blocks);  // uint2 entries the trace kernels need for a grid of that many blocks

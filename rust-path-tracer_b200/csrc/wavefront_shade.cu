@@ -8,13 +8,19 @@
 //               (lib.rs:225-226 / src/trace.rs:295-296)
 //   normalize   packed RGB framebuffer = output.xyz / samples (src/trace.rs:199-204)
 //
-// Materials are staged in shared memory once per persistent block.
+// Materials and — when they fit kSmemLightBytes — the light bins and light records are staged in shared memory once
+// per persistent block (kernels/src/light_pick.rs:8-16 reads one bin and one record per NEE sample, the MIS term
+// one record per emitter hit).
 #include "device_scene.h"
 
 namespace rpt {
 
 constexpr int kShadeBlock = 256;
 constexpr uint32_t kSmemMaterials = 64;  // 6 KB
+
+// A light-table word: plain (shared-memory) load when the table is staged, read-only global load otherwise.
+template <bool SMEM, class T>
+__device__ __forceinline__ T ldl(const T* p) { return SMEM ? *p : __ldg(p); }
 
 __device__ __forceinline__ uint32_t wave_pixel(const WaveDesc& d, uint32_t j) {
     const uint32_t i = d.pix_base + j;
@@ -25,15 +31,23 @@ __device__ __forceinline__ uint32_t wave_pixel(const WaveDesc& d, uint32_t j) {
 // q_shaded[i] = slot | kShadedNoNext | kShadedShadow (i = the hit's position in q_hit) and
 // wf_compact_shaded_kernel turns those words into the next extend queue and the shadow queue, in order.
 // The shadow ray itself is stored at index i (sh_o / sh_d / sh_c), the next ray in the path's own slot.
-template <bool MATS_IN_SMEM>
+template <bool MATS_IN_SMEM, bool LIGHTS_IN_SMEM, bool TANGENTS>
 __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f, WideWorld w, WaveState s, WaveDesc d, const uint2* __restrict__ rng,
                                                                uint32_t bounce) {
     __shared__ RptMaterialData sm_materials[MATS_IN_SMEM ? kSmemMaterials : 1];
+    __shared__ __align__(16) uint32_t sm_lights[LIGHTS_IN_SMEM ? kSmemLightBytes / 4 : 4];  // records first (16-byte aligned), then bins
     if (MATS_IN_SMEM) {
         const uint32_t words = w.nmaterials * (uint32_t)(sizeof(RptMaterialData) / 4);
         for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(sm_materials)[i] = reinterpret_cast<const uint32_t*>(w.materials)[i];
-        __syncthreads();
     }
+    if (LIGHTS_IN_SMEM) {
+        const uint32_t rec_words = w.nlights * (uint32_t)(sizeof(LightRecord) / 4), bin_words = w.nbins * (uint32_t)(sizeof(LightBin) / 4);
+        for (uint32_t i = threadIdx.x; i < rec_words; i += blockDim.x) sm_lights[i] = reinterpret_cast<const uint32_t*>(w.lights)[i];
+        for (uint32_t i = threadIdx.x; i < bin_words; i += blockDim.x) sm_lights[rec_words + i] = reinterpret_cast<const uint32_t*>(w.light_bins)[i];
+    }
+    if (MATS_IN_SMEM || LIGHTS_IN_SMEM) __syncthreads();
+    const LightRecord* const lights = LIGHTS_IN_SMEM ? reinterpret_cast<const LightRecord*>(sm_lights) : w.lights;
+    const LightBin* const light_bins = LIGHTS_IN_SMEM ? reinterpret_cast<const LightBin*>(sm_lights + w.nlights * (uint32_t)(sizeof(LightRecord) / 4)) : w.light_bins;
     const uint32_t n = s.ctl->n_hit;
     const bool nee = f.nee != RPT_NEE_NONE;
     const bool last_bounce = bounce + 1u >= f.max_bounces;
@@ -63,9 +77,10 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
         const uint2 seed = __ldg(rng + wave_pixel(d, slot % d.npix));
         Rng rstate{seed.x + slot / d.npix + seed.y, flags & 0xFFu};
 
-        const float4* tp = w.bvh.tri_pos + 3u * (size_t)tri;
-        const float4 a4 = __ldg(tp), e14 = __ldg(tp + 1), e24 = __ldg(tp + 2);
-        const RptMaterialData& mat = MATS_IN_SMEM ? sm_materials[__float_as_uint(e14.w)] : w.materials[__float_as_uint(e14.w)];
+        // the hit triangle's shading record: one aligned run of sectors (device_scene.h)
+        const float4* rec = w.tri_shade + (size_t)(TANGENTS ? kShadeStrideTangents : kShadeStridePlain) * tri;
+        const float4 a4 = __ldg(rec), e14 = __ldg(rec + 1), e24 = __ldg(rec + 2);
+        const RptMaterialData& mat = MATS_IN_SMEM ? sm_materials[__float_as_uint(a4.w)] : w.materials[__float_as_uint(a4.w)];
         const f3 emissive = mk3(mat.emissive[0], mat.emissive[1], mat.emissive[2]);
         const f3 hit = ro + rd * t;
         bool alive = true;
@@ -86,13 +101,13 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
                 // product is the current throughput times the Russian-roulette probability it was divided by
                 // (o4.w; 1 when no roulette ran), so no per-path copy of either factor is kept.
                 f3 c = splat3(0.0f);
-                const LightRecord& L = w.lights[w.nbins > 0u ? flags >> 9 : 0u];
-                if (w.nbins > 0u && tri == __float_as_uint(__ldg(&L.e2_tri).w)) {
-                    const float4 la = __ldg(&L.a_area);
-                    const float lp = light_pdf(la.w, t, xyz(__ldg(&L.normal)), rd);
+                const LightRecord& L = lights[w.nbins > 0u ? flags >> 9 : 0u];
+                if (w.nbins > 0u && tri == __float_as_uint(ldl<LIGHTS_IN_SMEM>(&L.e2_tri).w)) {
+                    const float4 la = ldl<LIGHTS_IN_SMEM>(&L.a_area);
+                    const float lp = light_pdf(la.w, t, xyz(ldl<LIGHTS_IN_SMEM>(&L.normal)), rd);
                     if (lp > 0.0f) {
                         const float wgt = power_heuristic(thr4.w, lp);
-                        c = (throughput * o4.w) * ((xyz(__ldg(&L.emission)) * wgt) / __ldg(&L.e1_pdf).w);
+                        c = (throughput * o4.w) * ((xyz(ldl<LIGHTS_IN_SMEM>(&L.emission)) * wgt) / ldl<LIGHTS_IN_SMEM>(&L.e1_pdf).w);
                     }
                 }
                 c = mask_nan(c);
@@ -106,16 +121,15 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
 
         if (alive) {
             // lib.rs:111-129 — barycentrics re-derived from the hit point; normal not renormalised
-            const float4* sp = w.tri_shade + 4u * (size_t)tri;
-            const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2), s3 = __ldg(sp + 3);
+            const float4 na = __ldg(rec + 3), nb = __ldg(rec + 4), nc = __ldg(rec + 5), r6 = __ldg(rec + 6);
             const f3 bary = barycentric(hit, xyz(a4), xyz(e14), xyz(e24));
-            f3 normal = (bary.x * xyz(s0) + bary.y * xyz(s1)) + bary.z * xyz(s2);
-            f2 uv{(bary.x * s0.w + bary.y * s2.w) + bary.z * s3.y, (bary.x * s1.w + bary.y * s3.x) + bary.z * s3.z};
+            f3 normal = (bary.x * xyz(na) + bary.y * xyz(nb)) + bary.z * xyz(nc);
+            f2 uv{(bary.x * e14.w + bary.y * na.w) + bary.z * nc.w, (bary.x * e24.w + bary.y * nb.w) + bary.z * r6.x};
             if (fminf(fmaxf(uv.x, 0.0f), 1.0f) != uv.x || fminf(fmaxf(uv.y, 0.0f), 1.0f) != uv.y) uv = f2{uv.x - floorf(uv.x), uv.y - floorf(uv.y)};
-            if (mat.has_normal_texture && w.tri_tangent) {  // lib.rs:131-141
+            if (TANGENTS && mat.has_normal_texture) {  // lib.rs:131-141
                 const f3 nm = f.atlas.sample(mat.normals, uv) * 2.0f - splat3(1.0f);
-                const float4* tg = w.tri_tangent + 3u * (size_t)tri;
-                const f3 tangent = (bary.x * xyz(__ldg(tg)) + bary.y * xyz(__ldg(tg + 1))) + bary.z * xyz(__ldg(tg + 2));
+                const float4 r7 = __ldg(rec + 7), r8 = __ldg(rec + 8);
+                const f3 tangent = (bary.x * mk3(r6.y, r6.z, r6.w) + bary.y * xyz(r7)) + bary.z * mk3(r7.w, r8.x, r8.y);
                 const f3 bitangent = cross(tangent, normal);
                 normal = normalize((tangent * nm.x + bitangent * nm.y) + normal * nm.z);
             }
@@ -130,11 +144,11 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
                 const float l1 = rstate.next(), l2 = rstate.next();
                 uint32_t bin_i = (uint32_t)fminf(l1 * (float)w.nbins, 4294967040.0f);
                 bin_i = min(bin_i, w.nbins - 1u);  // l1 == 1.0 would index one past the end (CPU path panics)
-                const LightBin* bp = w.light_bins + bin_i;
-                const LightBin bin{__ldg(&bp->light_a), __ldg(&bp->light_b), __ldg(&bp->ratio)};
+                const LightBin* bp = light_bins + bin_i;
+                const LightBin bin{ldl<LIGHTS_IN_SMEM>(&bp->light_a), ldl<LIGHTS_IN_SMEM>(&bp->light_b), ldl<LIGHTS_IN_SMEM>(&bp->ratio)};
                 light_rec = l2 < bin.ratio ? bin.light_a : bin.light_b;
-                const LightRecord& L = w.lights[light_rec];
-                const float4 la = __ldg(&L.a_area), le1 = __ldg(&L.e1_pdf), le2 = __ldg(&L.e2_tri);
+                const LightRecord& L = lights[light_rec];
+                const float4 la = ldl<LIGHTS_IN_SMEM>(&L.a_area), le1 = ldl<LIGHTS_IN_SMEM>(&L.e1_pdf), le2 = ldl<LIGHTS_IN_SMEM>(&L.e2_tri);
                 const float q1 = rstate.next(), q2 = rstate.next();
                 const float sq = sqrtf(q1);
                 // (1-sq) a + sq(1-q2) b + sq q2 c  ==  a + sq(1-q2) e1 + sq q2 e2
@@ -142,14 +156,14 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
                 const f3 to_light = lp - hit;
                 const float dist = length(to_light);
                 const f3 l = to_light / dist;
-                const float lpdf = light_pdf(la.w, dist, xyz(__ldg(&L.normal)), l);
+                const float lpdf = light_pdf(la.w, dist, xyz(ldl<LIGHTS_IN_SMEM>(&L.normal)), l);
                 if (lpdf > 0.0f) {
                     f3 fd;
                     float bpdf;
                     pbr_eval_diffuse(bsdf, view, normal, l, fd, bpdf);
                     if (bpdf > 0.0f) {
                         const float wgt = f.nee == RPT_NEE_MIS ? power_heuristic(lpdf, bpdf) : 1.0f;
-                        const f3 direct = (fd * xyz(__ldg(&L.emission)) * wgt / lpdf) / le1.w;
+                        const f3 direct = (fd * xyz(ldl<LIGHTS_IN_SMEM>(&L.emission)) * wgt / lpdf) / le1.w;
                         const f3 c = throughput * direct;
                         // a zero or non-finite contribution adds nothing whether or not the light is visible
                         if (finite3(c) && !zero3(c)) {
@@ -229,8 +243,18 @@ __global__ void wf_reset_kernel(WaveState s, int next_queue, bool whole) {
 
 void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld& w, const WaveState& s, const WaveDesc& d, const uint2* rng,
                      uint32_t bounce) {
-    if (w.nmaterials <= kSmemMaterials) wf_shade_kernel<true><<<l.grid * 4, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce);
-    else wf_shade_kernel<false><<<l.grid * 4, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce);
+    const bool mats = w.nmaterials <= kSmemMaterials;
+    const bool lights = w.nbins > 0u && (size_t)w.nlights * sizeof(LightRecord) + (size_t)w.nbins * sizeof(LightBin) <= kSmemLightBytes;
+    const bool tangents = w.shade_stride == kShadeStrideTangents;
+    const dim3 grid(l.grid * 4);
+#define RPT_SHADE(M, L, T) wf_shade_kernel<M, L, T><<<grid, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce)
+    if (mats && lights && tangents) RPT_SHADE(true, true, true);
+    else if (mats && lights) RPT_SHADE(true, true, false);
+    else if (mats && tangents) RPT_SHADE(true, false, true);
+    else if (mats) RPT_SHADE(true, false, false);
+    else if (tangents) RPT_SHADE(false, false, true);   // (more than 64 materials: everything from global memory)
+    else RPT_SHADE(false, false, false);
+#undef RPT_SHADE
 }
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole) { wf_reset_kernel<<<1, 32, 0, l.stream>>>(s, next_queue, whole); }
 void launch_wf_miss_procedural(const WaveLaunch& l, const FrameParams& f, const WaveState& s) {

@@ -158,6 +158,132 @@ __global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh,
     }
 }
 
+// ---- extend / shadow-connect with DEFERRED triangle tests -------------------------------------------------------
+// In the kernel above a lane tests the triangles of a visit right after the visit, so the ray/triangle code runs for
+// the two or three lanes of a warp that happen to have found a leaf in that round: it is a third of the kernel's
+// instructions at a tenth of its width.  Here a visit only QUEUES its triangles (wide indices, a per-lane stack of
+// kPendingCapacity words in shared memory) and the lane goes on traversing; the warp, which stays converged round by
+// round, runs triangle rounds when at least `flush_at` lanes hold a queued triangle — or when no lane has a node
+// left to visit — and keeps running them while at least `flush_keep` lanes still do; what is left stays queued for
+// the next flush.  A ray whose traversal is over keeps its slot until its queue is empty.  Modelled on the CPU first
+// (tools/warp_sim.py partial, harness_warp_sim2): triangle rounds 2.1 -> 0.65 per ray at 11 instead of 3 lanes, for
+// 2 % more node visits (the culling bound is refreshed later) and node rounds 5 % narrower (waiting lanes).
+// Results are the in-order kernel's, except that among hits with bit-equal t the smallest wide triangle index wins
+// (test_one<true>): the order in which a ray's candidates are tested depends on the other lanes here.
+constexpr int kPendingCapacity = 4;  // triangle groups (one per visit that found any) a lane can hold besides the cursor's own
+
+template <bool NEAREST, bool DEEP>
+__global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_deferred_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
+                                                                        int refill_below, int flush_at, int flush_keep, uint2* stack_overflow) {
+    __shared__ uint2 slabs[kTraceWarps][kWideStackShared][32];
+    // queued groups, as visit_node leaves them in the cursor: first triangle of the node, hit mask, valid mask
+    __shared__ uint32_t pending[kTraceWarps][kPendingCapacity][3][32];
+    __shared__ uint8_t perm_table[8 * 256];
+    for (uint32_t i = threadIdx.x; i < 8u * 256u; i += kTraceBlock) perm_table[i] = (uint8_t)octant_permute(i >> 8, i & 0xFFu);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t n = NEAREST ? (identity ? n_identity : (in_queue ? s.ctl->n_ext[1] : s.ctl->n_ext[0])) : s.ctl->n_shadow;
+    const uint32_t* __restrict__ queue = in_queue ? s.q_ext[1] : s.q_ext[0];
+    uint32_t* fetch = NEAREST ? &s.ctl->fetch_extend : &s.ctl->fetch_shadow;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.counters + (NEAREST ? 1 : 2), (unsigned long long)n);
+
+    SmemStack<DEEP> st{&slabs[warp][0][lane], 0, perm_table, DEEP ? stack_overflow + (size_t)blockIdx.x * kTraceBlock + threadIdx.x : nullptr,
+                       gridDim.x * kTraceBlock};
+    uint32_t* const pend = &pending[warp][0][0][lane];  // group g, word w at pend[(3 g + w) * 32]
+    int qn = 0;                                          // queued groups (the cursor's own group comes on top of these)
+    WideCursor<NEAREST> c;
+    uint32_t item = 0;
+    bool busy = false;
+    bool exhausted = false;
+    constexpr uint32_t kAll = 0xFFFFFFFFu;
+
+    for (;;) {
+        // ---- refill idle lanes (as in wf_trace_kernel)
+        if (!exhausted) {
+            const uint32_t idle = __ballot_sync(kAll, !busy);
+            if (idle) {
+                const int leader = __ffs((int)idle) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+                base = __shfl_sync(kAll, base, leader);
+                const uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                exhausted = base + (uint32_t)__popc(idle) >= n;
+                if (!busy && i < n) {
+                    float4 o, dv;
+                    float max_t = 0.0f;
+                    if (NEAREST) {
+                        item = identity ? i : __ldg(queue + i);
+                        o = s.ray_o[item];
+                        dv = s.ray_d[item];
+                    } else {
+                        item = __ldg(s.q_shadow + i);
+                        o = s.sh_o[item];
+                        dv = s.sh_d[item];
+                        max_t = o.w;
+                    }
+                    c.begin(xyz(o), xyz(dv), max_t);
+                    st.n = 0;
+                    qn = 0;
+                    busy = true;
+                }
+            }
+        }
+        uint32_t live = __ballot_sync(kAll, busy);
+        if (live == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- converged rounds until the warp wants a refill
+        for (;;) {
+            // node round: a lane walks on if it has a node and room to keep what the visit may find
+            const bool walking = busy && c.has_nodes() && (c.tgroup.y == 0u || qn < kPendingCapacity);
+            if (walking) {
+                if (c.tgroup.y != 0u) {  // the group of an earlier visit moves from the cursor to the queue
+                    pend[(3 * qn + 0) * 32] = c.tgroup.x;
+                    pend[(3 * qn + 1) * 32] = c.tgroup.y;
+                    pend[(3 * qn + 2) * 32] = c.tvalid;
+                    ++qn;
+                }
+                c.visit_node(bvh, st);
+            }
+            const bool has_work = busy && (c.tgroup.y != 0u || qn > 0);
+            uint32_t holding = __ballot_sync(kAll, has_work);
+            // flush when enough lanes hold triangles, or when nobody walked this round (every live lane waits for its triangles)
+            if (holding != 0u && (__popc(holding) >= flush_at || __ballot_sync(kAll, walking) == 0u)) {
+                do {
+                    if (busy) {
+                        if (c.tgroup.y == 0u && qn > 0) {
+                            --qn;
+                            c.tgroup.x = pend[(3 * qn + 0) * 32];
+                            c.tgroup.y = pend[(3 * qn + 1) * 32];
+                            c.tvalid = pend[(3 * qn + 2) * 32];
+                        }
+                        if (c.tgroup.y != 0u && c.template test_next<true>(bvh)) {  // true: an any-hit ray is decided
+                            c.abandon(st);
+                            qn = 0;
+                        }
+                    }
+                    holding = __ballot_sync(kAll, busy && (c.tgroup.y != 0u || qn > 0));
+                } while (__popc(holding) >= flush_keep);
+            }
+            if (busy && !c.has_nodes() && c.tgroup.y == 0u && qn == 0) {
+                busy = false;
+                if (NEAREST) {
+                    s.hit[item] = make_uint2(__float_as_uint(c.best_t), c.hit_tri);
+                } else if (c.hit_tri == kNoNode) {
+                    const uint32_t slot = __float_as_uint(s.sh_d[item].w);
+                    const float4 add = s.sh_c[item];
+                    float4 r = s.rad[slot];
+                    r.x += add.x; r.y += add.y; r.z += add.z;
+                    s.rad[slot] = r;
+                }
+            }
+            live = __ballot_sync(kAll, busy);
+            if (live == 0u || (!exhausted && __popc(live) < refill_below)) break;
+        }
+    }
+}
+
 // ---- order-preserving two-way stream compaction ------------------------------------------------
 // Both compaction kernels split one input stream into two output queues IN INPUT ORDER (the shading stages
 // then read path state coalesced although rays finish in any order).  A block handles kCompactItems
@@ -278,7 +404,11 @@ void launch_wf_generate(const WaveLaunch& l, const FrameParams& f, const WaveSta
     wf_generate_kernel<<<l.grid * 8, 256, 0, l.stream>>>(f, s, d, rng);
 }
 void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, int in_queue, bool identity_queue, uint32_t n_identity) {
-    if (l.stack_overflow)
+    if (l.defer_extend && l.stack_overflow)
+        wf_trace_deferred_kernel<true, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.flush_at, l.flush_keep, l.stack_overflow);
+    else if (l.defer_extend)
+        wf_trace_deferred_kernel<true, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.flush_at, l.flush_keep, nullptr);
+    else if (l.stack_overflow)
         wf_trace_kernel<true, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.stack_overflow);
     else
         wf_trace_kernel<true, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, nullptr);
@@ -288,7 +418,11 @@ void launch_wf_compact_shaded(const WaveLaunch& l, const WaveState& s, int out_q
     wf_compact_shaded_kernel<<<l.grid * 8, kCompactBlock, 0, l.stream>>>(s, out_queue);
 }
 void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState& s) {
-    if (l.stack_overflow)
+    if (l.defer_shadow && l.stack_overflow)
+        wf_trace_deferred_kernel<false, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.flush_at, l.flush_keep, l.stack_overflow);
+    else if (l.defer_shadow)
+        wf_trace_deferred_kernel<false, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.flush_at, l.flush_keep, nullptr);
+    else if (l.stack_overflow)
         wf_trace_kernel<false, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.stack_overflow);
     else
         wf_trace_kernel<false, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, nullptr);

@@ -273,4 +273,97 @@ int harness_warp_sim(const RptPerVertexData* verts, uint32_t nverts, const uint3
     out[0] = node_rounds; out[1] = lane_visits; out[2] = tri_rounds; out[3] = lane_tests; out[4] = nrays; out[5] = refills;
     return 0;
 }
+
+// Experiment 2 (round 2): deferred triangle tests with a per-lane queue of pending triangles and PARTIAL flushes.
+// After every node round the warp counts the lanes that hold a pending triangle; triangle rounds start when at least
+// `t_hi` lanes do (or `blocked_at` lanes have finished walking and only wait for their triangles, or a lane's queue
+// is full, or no lane can visit a node) and go on while at least `t_lo` lanes still do — the rest stays queued for a
+// later flush, so a triangle round never runs narrower than t_lo lanes unless it is forced.  A lane whose traversal is
+// over keeps its queue and waits (it counts towards the thresholds).  capacity < 0: LIFO queue, else FIFO.
+// out as harness_warp_sim, plus [7] forced triangle rounds.
+int harness_warp_sim2(const RptPerVertexData* verts, uint32_t nverts, const uint32_t* tris, uint32_t ntris, const RptBVHNode* nodes, uint32_t nnodes,
+                      const float* rays_o_d, uint32_t nrays, int refill_below, int t_hi, int t_lo, int capacity, int blocked_at, uint64_t* out) {
+    rpt::WideBvh wide;
+    const char* err = "";
+    if (!rpt::build_wide_bvh(nodes, nnodes, tris, ntris, verts, nverts, wide, &err)) return -1;
+    rpt::WideScene scene{reinterpret_cast<const rpt::uint4*>(wide.nodes.data()), reinterpret_cast<const rpt::float4*>(wide.tri_pos.data()), rpt::kHalf1024Bytes};
+    struct Lane {
+        rpt::WideCursor<true> c;
+        LocalStack st;
+        bool busy = false;
+        uint32_t ray = 0;
+        std::vector<uint32_t> queue;  // pending triangles (wide indices)
+    };
+    std::vector<Lane> lanes(32);
+    uint64_t node_rounds = 0, lane_visits = 0, tri_rounds = 0, lane_tests = 0, refills = 0, wrong = 0, forced = 0;
+    uint32_t fetch = 0;
+    auto live = [&] { int n = 0; for (const Lane& l : lanes) n += l.busy; return n; };
+    auto holding = [&] { int n = 0; for (const Lane& l : lanes) n += l.busy && !l.queue.empty(); return n; };
+    auto tri_round = [&] {
+        int active = 0;
+        for (Lane& l : lanes) {
+            if (!l.busy || l.queue.empty()) continue;
+            uint32_t ti;
+            if (capacity < 0) { ti = l.queue.back(); l.queue.pop_back(); }
+            else { ti = l.queue.front(); l.queue.erase(l.queue.begin()); }
+            l.c.tgroup = rpt::make_uint2(ti, 1u);  // a one-bit group whose rank-0 triangle is ti
+            l.c.tvalid = 1u;
+            l.c.test_triangle(scene);
+            ++active;
+        }
+        if (active) { ++tri_rounds; lane_tests += (uint64_t)active; }
+        return active;
+    };
+    for (;;) {
+        if (fetch < nrays && live() < refill_below) {
+            ++refills;
+            for (Lane& l : lanes) {
+                if (l.busy || fetch >= nrays) continue;
+                l.ray = fetch;
+                const float* r = rays_o_d + 6 * (size_t)fetch++;
+                l.c.begin(rpt::mk3(r[0], r[1], r[2]), rpt::mk3(r[3], r[4], r[5]), 0.0f);
+                l.st.clear();
+                l.queue.clear();
+                l.busy = true;
+            }
+        }
+        if (live() == 0) break;
+        int visiting = 0;
+        bool full = false;
+        for (Lane& l : lanes) {
+            if (!l.busy || !l.c.has_nodes()) continue;
+            if ((int)l.queue.size() + 6 > std::abs(capacity)) { full = true; continue; }
+            l.c.visit_node(scene, l.st);
+            ++visiting;
+            while (l.c.has_triangles()) {
+                const int k = rpt::highest_bit(l.c.tgroup.y);
+                l.c.tgroup.y &= ~(1u << k);
+                l.queue.push_back(l.c.tgroup.x + (uint32_t)rpt::popcount(l.c.tvalid & ~(0xFFFFFFFFu << k)));
+            }
+        }
+        if (visiting) { ++node_rounds; lane_visits += (uint64_t)visiting; }
+        int h = holding();
+        int blocked = 0;
+        for (const Lane& l : lanes) blocked += l.busy && !l.c.has_nodes() && !l.queue.empty();
+        if (h >= t_hi) {
+            while (h >= t_lo && tri_round()) h = holding();
+        } else if (blocked >= blocked_at) {
+            do { tri_round(); h = holding(); } while (h >= t_lo);
+        } else if ((full || visiting == 0) && h > 0) {
+            do { tri_round(); ++forced; h = holding(); } while (h >= t_lo);
+        }
+        for (Lane& l : lanes)
+            if (l.busy && !l.c.has_nodes() && l.queue.empty()) {
+                l.busy = false;
+                const float* r = rays_o_d + 6 * (size_t)l.ray;
+                LocalStack st;
+                const rpt::WideHit want = rpt::wide_intersect<true>(scene, rpt::mk3(r[0], r[1], r[2]), rpt::mk3(r[3], r[4], r[5]), 0.0f, st);
+                const rpt::WideHit got = l.c.result();
+                if (got.hit != want.hit || (got.hit && (got.triangle != want.triangle || std::memcmp(&got.t, &want.t, 4) != 0 || got.backface != want.backface))) ++wrong;
+            }
+    }
+    out[6] = wrong; out[7] = forced;
+    out[0] = node_rounds; out[1] = lane_visits; out[2] = tri_rounds; out[3] = lane_tests; out[4] = nrays; out[5] = refills;
+    return 0;
+}
 }

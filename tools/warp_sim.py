@@ -38,7 +38,28 @@ def sim(world, rays, refill_below, defer, slots=1):
             "tests/ray": lt / n, "instr/ray": (nr * NODE_INSTR + tr * TRI_INSTR) / n}
 
 
+def sim2(world, rays, refill_below, t_hi, t_lo, capacity, blocked_at=99):
+    out = np.zeros(8, np.uint64)
+    rc = lib.harness_warp_sim2(P(world.per_vertex_buffer), C.c_uint32(len(world.per_vertex_buffer)), P(world.index_buffer), C.c_uint32(len(world.index_buffer)),
+                               P(world.nodes), C.c_uint32(len(world.nodes)), P(rays), C.c_uint32(len(rays)), C.c_int(refill_below), C.c_int(t_hi), C.c_int(t_lo),
+                               C.c_int(capacity), C.c_int(blocked_at), P(out))
+    assert rc == 0, rc
+    nr, lv, tr, lt, n = (float(x) for x in out[:5])
+    return {"node_rounds/ray": nr / n, "lanes/node_round": lv / nr, "visits/ray": lv / n, "tri_rounds/ray": tr / n, "lanes/tri_round": lt / max(tr, 1),
+            "tests/ray": lt / n, "instr/ray": (nr * (NODE_INSTR + 12) + tr * (TRI_INSTR + 8)) / n, "wrong": float(out[6]), "forced": float(out[7]) / n}
+
+
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64000
+if len(sys.argv) > 2 and sys.argv[2] == "partial":
+    for name in ("breaktime", "cornell"):
+        world = bench.load_workload(name)[0]
+        rays = surface_rays(world, n)
+        r = sim(world, rays, 20, 0, 0)
+        print(f"{name:10s} as built:                        " + "  ".join(f"{k} {v:7.3f}" for k, v in r.items()), flush=True)
+        for t_hi, t_lo, cap, blk in ((12, 6, -16, 99), (12, 6, -16, 6), (12, 6, -16, 4), (12, 6, -16, 3), (12, 4, -16, 3), (16, 6, -16, 4), (12, 2, -16, 4), (12, 1, -16, 99)):
+            r = sim2(world, rays, 20, t_hi, t_lo, cap, blk)
+            print(f"{name:10s} start {t_hi:2d} keep {t_lo:2d} capacity {cap:2d} blocked {blk:2d}: " + "  ".join(f"{k} {v:7.3f}" for k, v in r.items()), flush=True)
+    sys.exit(0)
 for name in ("breaktime", "cornell"):
     world = bench.load_workload(name)[0]
     rays = surface_rays(world, n)
