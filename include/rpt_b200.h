@@ -123,6 +123,10 @@ int rpt_reset_counters(rpt_context* ctx);
  * rpt_reset_counters (CUDA events on the context's stream). */
 int rpt_get_device_ms(rpt_context* ctx, float* ms);
 
+/* Device time of a region of calls (enqueues and the combine) from CUDA events on the library's own streams. */
+int rpt_timer_start(rpt_context* ctx);
+int rpt_timer_stop(rpt_context* ctx, float* ms); /* waits for the region's work */
+
 /* Per-stage device time, for roofline accounting.  While enabled, every kernel launch of
  * rpt_enqueue is bracketed by CUDA events on the context's stream (this perturbs the pipeline a
  * little, so whole-job throughput is measured with it off). */
@@ -135,11 +139,30 @@ typedef struct RptStageTiming {
 int rpt_set_stage_timing(rpt_context* ctx, int enable);
 int rpt_get_stage_timing(rpt_context* ctx, RptStageTiming* out); /* syncs; clears the totals */
 
+/* Traversal statistics, for roofline accounting in the backend's OWN layout.  While enabled, rpt_enqueue launches a
+ * counting build of the trace kernels (a little slower; the product build carries no counters): node visits (one
+ * 80-byte wide node each) and ray/triangle tests (one 48-byte record each) since the last rpt_reset_counters. */
+typedef struct RptTraceStatistics {
+    uint64_t nearest_rays, nearest_node_visits, nearest_triangle_tests;
+    uint64_t any_rays, any_node_visits, any_triangle_tests;
+    uint64_t shaded_hits;               /* surface hits shaded (counted by the product build too) */
+    uint32_t node_bytes, triangle_bytes; /* bytes read per visit / per test */
+} RptTraceStatistics;
+int rpt_get_sm_count(rpt_context* ctx, int* sm_count); /* multiprocessors of the context's device (persistent grids are multiples of it) */
+int rpt_set_trace_statistics(rpt_context* ctx, int enable);
+int rpt_get_trace_statistics(rpt_context* ctx, RptTraceStatistics* out);
+
 /* ---- multi-GPU combine over NCCL (one rank per GPU) ------------------------------------- */
 /* id_bytes: 128-byte ncclUniqueId made by rank 0 and distributed by the host (any channel). */
 int rpt_comm_unique_id(uint8_t* id_bytes_128);
 int rpt_comm_init(rpt_context* ctx, const uint8_t* id_bytes_128, int rank, int nranks);
-/* Sum the per-rank accumulators into root's (ncclReduce over NVLink); other ranks unchanged. */
+/* Combine the per-rank accumulators on `root` over NVLink.  NO accumulator is modified (calling it twice combines the
+ * same samples twice into the same result): every rank snapshots its contribution on its render stream, the exchange
+ * runs on a side stream — the next rpt_enqueue overlaps it — and the result is root's COMBINED FRAME, which root's
+ * rpt_read_output / rpt_read_framebuffer / rpt_read_display* return from then on (they wait for the exchange);
+ * rpt_write_output or a resize drops it.  Whole-frame ranks (sample-index split): ncclReduce(sum).  Tile ranks
+ * (rpt_set_tile_partition(rank, nranks) on every rank): each rank sends only the pixels it owns (ncclSend / ncclRecv),
+ * root scatters them — bit-identical to one GPU. */
 int rpt_comm_reduce_output(rpt_context* ctx, int root);
 int rpt_comm_destroy(rpt_context* ctx);
 

@@ -27,7 +27,7 @@ DEVICE_SYMBOLS = [
     "rpt_create", "rpt_destroy", "rpt_last_error", "rpt_set_pipeline", "rpt_set_wave_slots", "rpt_upload_world",
     "rpt_set_config", "rpt_write_rng", "rpt_read_rng", "rpt_write_output", "rpt_set_tile_partition", "rpt_enqueue",
     "rpt_sync", "rpt_read_output", "rpt_read_framebuffer", "rpt_read_display", "rpt_read_display_rgba8", "rpt_read_primary_ids", "rpt_get_counters",
-    "rpt_reset_counters", "rpt_get_device_ms", "rpt_set_stage_timing", "rpt_get_stage_timing", "rpt_comm_unique_id", "rpt_comm_init", "rpt_comm_reduce_output",
+    "rpt_reset_counters", "rpt_get_device_ms", "rpt_set_stage_timing", "rpt_get_stage_timing", "rpt_set_trace_statistics", "rpt_get_trace_statistics", "rpt_get_sm_count", "rpt_timer_start", "rpt_timer_stop", "rpt_comm_unique_id", "rpt_comm_init", "rpt_comm_reduce_output",
     "rpt_comm_destroy", "rpt_host_alloc", "rpt_host_free",
 ]
 
@@ -74,6 +74,12 @@ assert C.sizeof(TracingConfig) == 80
 
 class Counters(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("nearest_rays", C.c_uint64), ("any_rays", C.c_uint64), ("kernel_launches", C.c_uint64)]
+
+
+class TraceStatistics(C.Structure):
+    _fields_ = [("nearest_rays", C.c_uint64), ("nearest_node_visits", C.c_uint64), ("nearest_triangle_tests", C.c_uint64),
+                ("any_rays", C.c_uint64), ("any_node_visits", C.c_uint64), ("any_triangle_tests", C.c_uint64), ("shaded_hits", C.c_uint64),
+                ("node_bytes", C.c_uint32), ("triangle_bytes", C.c_uint32)]
 
 
 STAGES = ["generate", "extend", "miss", "shade", "shadow", "accumulate", "megakernel", "other"]

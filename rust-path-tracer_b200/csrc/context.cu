@@ -69,6 +69,10 @@ struct NcclApi {
     int (*GetUniqueId)(NcclUniqueId*) = nullptr;
     int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
     int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool load(std::string& err) {
@@ -81,9 +85,13 @@ struct NcclApi {
         GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(handle, "ncclGetUniqueId"));
         CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(handle, "ncclCommInitRank"));
         Reduce = reinterpret_cast<decltype(Reduce)>(dlsym(handle, "ncclReduce"));
+        Send = reinterpret_cast<decltype(Send)>(dlsym(handle, "ncclSend"));
+        Recv = reinterpret_cast<decltype(Recv)>(dlsym(handle, "ncclRecv"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(handle, "ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(handle, "ncclGroupEnd"));
         CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
         GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
-        if (!GetUniqueId || !CommInitRank || !Reduce || !CommDestroy) { err = "libnccl is missing expected symbols"; return false; }
+        if (!GetUniqueId || !CommInitRank || !Reduce || !CommDestroy || !Send || !Recv || !GroupStart || !GroupEnd) { err = "libnccl is missing expected symbols"; return false; }
         return true;
     }
 };
@@ -176,6 +184,7 @@ struct rpt_context {
         ++graph_epoch;
     }
     bool stage_timing = false;
+    bool trace_statistics = false;  // rpt_set_trace_statistics: launch the counting build of the trace kernels
     struct StageEvent { int stage; cudaEvent_t e0, e1; };
     std::vector<StageEvent> stage_events;
     RptStageTiming stage_totals{};
@@ -201,9 +210,30 @@ struct rpt_context {
     }
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
     float device_ms = 0.0f;
+    cudaEvent_t region_start = nullptr, region_stop = nullptr;  // rpt_timer_start / rpt_timer_stop
 
     void* nccl_comm = nullptr;
     int nccl_rank = 0, nccl_nranks = 1;
+    // The combine never touches an accumulator: it snapshots this rank's contribution on the render stream, moves it
+    // over NVLink on `comm_stream` — overlapped with whatever the render stream does next — and leaves the combined frame
+    // in `d_combined` on the root, which the read calls then return (until rpt_write_output / a resize drops it).
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_snapshot = nullptr, ev_combined = nullptr;
+    DevBuf<float4> d_snapshot, d_combined, d_gather;  // d_gather (root, tile mode): every rank's packed tiles, rank after rank
+    bool combined_valid = false;
+    struct RankTiles { uint32_t count; DevBuf<uint32_t> map; };
+    std::vector<RankTiles> gather_maps;  // root, tile mode: the pixel map of every rank
+    uint32_t gather_w = 0, gather_h = 0;
+    void drop_gather_maps() {
+        for (auto& t : gather_maps) t.map.release();
+        gather_maps.clear();
+    }
+    // the frame the read calls return: the combined one after a combine (waits for it), else this context's accumulator
+    const float4* frame_for_read() {
+        if (!combined_valid) return d_output.p;
+        cudaStreamWaitEvent(stream, ev_combined, 0);
+        return d_combined.p;
+    }
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -370,7 +400,8 @@ int run_wave(rpt_context* c, const WaveDesc& d, bool primary_only, uint32_t* ids
     const WideWorld w = wide_world(c);
     const WaveState s = wave_state(c);
     const WaveLaunch l{c->sm_count, c->stream, c->trace_blocks_per_sm, c->refill_below, c->deep_tree ? c->w_stack_overflow.p : nullptr,
-                       c->defer_extend, c->defer_shadow, c->flush_at, std::max(1, c->flush_keep)};
+                       c->defer_extend && !c->trace_statistics, c->defer_shadow && !c->trace_statistics, c->flush_at, std::max(1, c->flush_keep),
+                       c->trace_statistics};
     const uint32_t nslots = d.npix * d.k_samples;
     c->launch(RPT_STAGE_OTHER, [&] { launch_wf_reset(l, s, 1, true); });
     c->launch(RPT_STAGE_GENERATE, [&] { launch_wf_generate(l, f, s, d, c->d_rng.p); });
@@ -477,8 +508,8 @@ extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
     c->device = device_id;
     cudaDeviceProp prop{};
     if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess || (e = c->d_counters.alloc(4)) != cudaSuccess ||
-        (e = cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess || (e = c->d_counters.alloc(8)) != cudaSuccess ||
+        (e = cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->stream)) != cudaSuccess) {
         g_create_error = std::string("device initialisation failed: ") + cudaGetErrorString(e);
         delete c;
         return RPT_ERR_CUDA;
@@ -509,8 +540,15 @@ extern "C" int rpt_destroy(rpt_context* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->drop_graphs();
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    if (c->ev_snapshot) cudaEventDestroy(c->ev_snapshot);
+    if (c->ev_combined) cudaEventDestroy(c->ev_combined);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    c->drop_gather_maps();
+    c->d_snapshot.release(); c->d_combined.release(); c->d_gather.release();
     for (auto& ev : c->timed) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    if (c->region_start) { cudaEventDestroy(c->region_start); cudaEventDestroy(c->region_stop); }
     c->drain_stage_events();
     for (auto* b : {&c->w_ray_o, &c->w_ray_d, &c->w_thr, &c->w_rad, &c->w_sh_o, &c->w_sh_d, &c->w_sh_c, &c->d_tri_pos,
                     &c->d_tri_shade, &c->d_sky, &c->d_output})
@@ -743,6 +781,10 @@ extern "C" int rpt_set_config(rpt_context* c, const RptTracingConfig* cfg) {
     c->sky_yaw_cos = std::cos(yaw);
     if (resized) {
         const size_t n = (size_t)cfg->width * cfg->height;
+        if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+        c->combined_valid = false;
+        c->d_snapshot.release(); c->d_combined.release(); c->d_gather.release();
+        c->drop_gather_maps();
         RPT_CUDA(c, c->d_rng.alloc(n));
         RPT_CUDA(c, c->d_output.alloc(n));
         RPT_CUDA(c, cudaMemsetAsync(c->d_output.p, 0, n * sizeof(float4), c->stream));
@@ -780,6 +822,7 @@ extern "C" int rpt_write_output(rpt_context* c, const float* rgba, size_t npixel
     if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "rpt_write_output before rpt_set_config");
     if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "output has %zu entries, frame has %u pixels", npixels, c->npixels());
     RPT_TRY(bind_device(c));
+    c->combined_valid = false;  // a reset / resume starts a new frame: reads return this context's accumulator again
     if (rgba) RPT_CUDA(c, cudaMemcpyAsync(c->d_output.p, rgba, npixels * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     else RPT_CUDA(c, cudaMemsetAsync(c->d_output.p, 0, npixels * sizeof(float4), c->stream));
     return c->cuda(cudaStreamSynchronize(c->stream), "rpt_write_output");
@@ -791,6 +834,8 @@ extern "C" int rpt_set_tile_partition(rpt_context* c, uint32_t tile_rank, uint32
     RPT_TRY(bind_device(c));
     c->tile_rank = tile_rank;
     c->tile_count = tile_count;
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+    c->drop_gather_maps();
     c->drop_graphs();
     return rebuild_pixel_map(c);
 }
@@ -867,6 +912,7 @@ extern "C" int rpt_enqueue(rpt_context* c, uint32_t n_samples) {
 extern "C" int rpt_sync(rpt_context* c) {
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
     RPT_TRY(bind_device(c));
+    if (c->comm_stream) RPT_CUDA(c, cudaStreamSynchronize(c->comm_stream));
     return c->cuda(cudaStreamSynchronize(c->stream), "rpt_sync");
 }
 
@@ -876,7 +922,7 @@ extern "C" int rpt_read_output(rpt_context* c, float* rgba, size_t npixels) {
     if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "rpt_read_output before rpt_set_config");
     if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "frame has %u pixels, caller asked for %zu", c->npixels(), npixels);
     RPT_TRY(bind_device(c));
-    RPT_CUDA(c, cudaMemcpyAsync(rgba, c->d_output.p, npixels * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    RPT_CUDA(c, cudaMemcpyAsync(rgba, c->frame_for_read(), npixels * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
     return c->cuda(cudaStreamSynchronize(c->stream), "rpt_read_output");
 }
 
@@ -886,7 +932,7 @@ extern "C" int rpt_read_framebuffer(rpt_context* c, float* rgb, size_t npixels, 
     if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "frame has %u pixels, caller asked for %zu", c->npixels(), npixels);
     RPT_TRY(bind_device(c));
     if (c->d_rgb.n != npixels * 3) RPT_CUDA(c, c->d_rgb.alloc(npixels * 3));
-    launch_normalize(c->d_output.p, c->d_rgb.p, (uint32_t)npixels, samples, c->stream);
+    launch_normalize(c->frame_for_read(), c->d_rgb.p, (uint32_t)npixels, samples, c->stream);
     c->kernel_launches++;
     RPT_CUDA(c, cudaGetLastError());
     RPT_CUDA(c, cudaMemcpyAsync(rgb, c->d_rgb.p, npixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -899,7 +945,7 @@ extern "C" int rpt_read_display(rpt_context* c, float* rgb, size_t npixels, floa
     if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "frame has %u pixels, caller asked for %zu", c->npixels(), npixels);
     RPT_TRY(bind_device(c));
     if (c->d_rgb.n != npixels * 3) RPT_CUDA(c, c->d_rgb.alloc(npixels * 3));
-    launch_display(c->d_output.p, c->d_rgb.p, (uint32_t)npixels, samples, tonemap, c->stream);
+    launch_display(c->frame_for_read(), c->d_rgb.p, (uint32_t)npixels, samples, tonemap, c->stream);
     c->kernel_launches++;
     RPT_CUDA(c, cudaGetLastError());
     RPT_CUDA(c, cudaMemcpyAsync(rgb, c->d_rgb.p, npixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -912,7 +958,7 @@ extern "C" int rpt_read_display_rgba8(rpt_context* c, uint8_t* rgba, size_t npix
     if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "frame has %u pixels, caller asked for %zu", c->npixels(), npixels);
     RPT_TRY(bind_device(c));
     if (c->d_rgba8.n != npixels) RPT_CUDA(c, c->d_rgba8.alloc(npixels));
-    launch_display_rgba8(c->d_output.p, c->d_rgba8.p, (uint32_t)npixels, samples, tonemap, srgb_encode != 0, c->stream);
+    launch_display_rgba8(c->frame_for_read(), c->d_rgba8.p, (uint32_t)npixels, samples, tonemap, srgb_encode != 0, c->stream);
     c->kernel_launches++;
     RPT_CUDA(c, cudaGetLastError());
     RPT_CUDA(c, cudaMemcpyAsync(rgba, c->d_rgba8.p, npixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -926,7 +972,7 @@ extern "C" int rpt_read_primary_ids(rpt_context* c, uint32_t* ids, size_t npixel
     if (c->d_ids.n != npixels) RPT_CUDA(c, c->d_ids.alloc(npixels));
     RPT_CUDA(c, cudaMemsetAsync(c->d_ids.p, 0xFF, npixels * sizeof(uint32_t), c->stream));
     // counters must not move for a diagnostic pass: save and restore them around it
-    unsigned long long saved[4];
+    unsigned long long saved[8];
     RPT_CUDA(c, cudaMemcpyAsync(saved, c->d_counters.p, sizeof saved, cudaMemcpyDeviceToHost, c->stream));
     RPT_CUDA(c, cudaStreamSynchronize(c->stream));
     int status = RPT_OK;
@@ -963,7 +1009,7 @@ extern "C" int rpt_get_counters(rpt_context* c, RptCounters* out) {
 extern "C" int rpt_reset_counters(rpt_context* c) {
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
     RPT_TRY(bind_device(c));
-    RPT_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    RPT_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
     RPT_CUDA(c, cudaStreamSynchronize(c->stream));
     for (auto& ev : c->timed) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     c->timed.clear();
@@ -986,6 +1032,60 @@ extern "C" int rpt_get_device_ms(rpt_context* c, float* ms) {
     c->timed.clear();
     *ms = c->device_ms;
     return RPT_OK;
+}
+
+extern "C" int rpt_get_sm_count(rpt_context* c, int* sm_count) {
+    if (!c || !sm_count) return RPT_ERR_INVALID_ARGUMENT;
+    *sm_count = c->sm_count;
+    return RPT_OK;
+}
+
+extern "C" int rpt_set_trace_statistics(rpt_context* c, int enable) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    if (c->trace_statistics != (enable != 0)) c->drop_graphs();  // the captured waves launch the other build
+    c->trace_statistics = enable != 0;
+    return RPT_OK;
+}
+
+extern "C" int rpt_get_trace_statistics(rpt_context* c, RptTraceStatistics* out) {
+    if (!c || !out) return RPT_ERR_INVALID_ARGUMENT;
+    RPT_TRY(bind_device(c));
+    unsigned long long host[8] = {0};
+    RPT_CUDA(c, cudaMemcpyAsync(host, c->d_counters.p, sizeof host, cudaMemcpyDeviceToHost, c->stream));
+    RPT_CUDA(c, cudaStreamSynchronize(c->stream));
+    out->nearest_rays = host[1];
+    out->any_rays = host[2];
+    out->nearest_node_visits = host[4];
+    out->nearest_triangle_tests = host[5];
+    out->any_node_visits = host[6];
+    out->any_triangle_tests = host[7];
+    out->shaded_hits = host[3];
+    out->node_bytes = sizeof(WideNode);
+    out->triangle_bytes = 48;
+    return RPT_OK;
+}
+
+// Device time of a region of calls — enqueues AND the combine on the side stream — from CUDA events on the streams the
+// work is launched on (bench.py times multi-GPU steps with this, never by wall clock).
+extern "C" int rpt_timer_start(rpt_context* c) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    RPT_TRY(bind_device(c));
+    if (!c->region_start) {
+        RPT_CUDA(c, cudaEventCreate(&c->region_start));
+        RPT_CUDA(c, cudaEventCreate(&c->region_stop));
+    }
+    if (c->comm_stream) RPT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_combined, 0));  // an earlier combine is not part of the region
+    return c->cuda(cudaEventRecord(c->region_start, c->stream), "rpt_timer_start");
+}
+
+extern "C" int rpt_timer_stop(rpt_context* c, float* ms) {
+    if (!c || !ms) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->region_start) return c->fail(RPT_ERR_NOT_READY, "rpt_timer_stop before rpt_timer_start");
+    RPT_TRY(bind_device(c));
+    if (c->comm_stream) RPT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_combined, 0));  // the region ends when the combine has landed
+    RPT_CUDA(c, cudaEventRecord(c->region_stop, c->stream));
+    RPT_CUDA(c, cudaEventSynchronize(c->region_stop));
+    return c->cuda(cudaEventElapsedTime(ms, c->region_start, c->region_stop), "rpt_timer_stop");
 }
 
 extern "C" int rpt_set_stage_timing(rpt_context* c, int enable) {
@@ -1032,14 +1132,104 @@ extern "C" int rpt_comm_init(rpt_context* c, const uint8_t* id_bytes_128, int ra
     return RPT_OK;
 }
 
+namespace {
+int nccl_fail(rpt_context* c, int r, const char* what) {
+    return c->fail(RPT_ERR_NCCL, "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+}
+
+int ensure_comm_stream(rpt_context* c) {
+    if (c->comm_stream) return RPT_OK;
+    RPT_CUDA(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    RPT_CUDA(c, cudaEventCreateWithFlags(&c->ev_snapshot, cudaEventDisableTiming));
+    RPT_CUDA(c, cudaEventCreateWithFlags(&c->ev_combined, cudaEventDisableTiming));
+    return RPT_OK;
+}
+}  // namespace
+
+// Combine the per-rank accumulators on `root`.  No accumulator is modified: each rank snapshots its contribution on
+// the render stream, the exchange runs on a side stream (so the next rpt_enqueue overlaps it), and the result is
+// the root's "combined frame", which its read calls return from then on (rpt_write_output or a resize drops it).
+//   * whole-frame ranks (sample-index split): snapshot = the accumulator; ncclReduce(sum) over NVLink.
+//   * tile ranks (rpt_set_tile_partition(rank, nranks)): snapshot = the pixels this rank owns, packed; every rank
+//     sends its pack to the root (grouped ncclSend / ncclRecv), which scatters them: (nranks - 1) / nranks of ONE
+//     frame crosses NVLink instead of a reduce over nranks full frames of mostly zeros.  Bit-identical to one GPU.
 extern "C" int rpt_comm_reduce_output(rpt_context* c, int root) {
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
     if (!c->nccl_comm) return c->fail(RPT_ERR_NOT_READY, "rpt_comm_reduce_output before rpt_comm_init");
     if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "no frame to reduce");
+    if (root < 0 || root >= c->nccl_nranks) return c->fail(RPT_ERR_INVALID_ARGUMENT, "root %d of %d ranks", root, c->nccl_nranks);
     RPT_TRY(bind_device(c));
-    // per-GPU accumulators (sum rgb, sample count in w) add up to the single-GPU accumulator; in place on root
-    const int r = g_nccl.Reduce(c->d_output.p, c->d_output.p, (size_t)c->npixels() * 4, /*ncclFloat32*/ 7, /*ncclSum*/ 0, root, c->nccl_comm, c->stream);
-    if (r != 0) return c->fail(RPT_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    RPT_TRY(ensure_comm_stream(c));
+    const uint32_t npix = c->npixels();
+    const bool is_root = c->nccl_rank == root;
+    const bool tiles = c->tile_count > 1;
+    if (tiles && ((int)c->tile_count != c->nccl_nranks || (int)c->tile_rank != c->nccl_rank))
+        return c->fail(RPT_ERR_INVALID_ARGUMENT, "tile partition %u of %u does not match rank %d of %d", c->tile_rank, c->tile_count, c->nccl_rank, c->nccl_nranks);
+    // the previous combine must be off the wire before its buffers are reused
+    RPT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_combined, 0));
+    if (is_root && c->d_combined.n != npix) RPT_CUDA(c, c->d_combined.alloc(npix));
+
+    if (!tiles) {
+        if (c->d_snapshot.n != npix) RPT_CUDA(c, c->d_snapshot.alloc(npix));
+        RPT_CUDA(c, cudaMemcpyAsync(c->d_snapshot.p, c->d_output.p, (size_t)npix * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        RPT_CUDA(c, cudaEventRecord(c->ev_snapshot, c->stream));
+        RPT_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_snapshot, 0));
+        const int r = g_nccl.Reduce(c->d_snapshot.p, is_root ? c->d_combined.p : nullptr, (size_t)npix * 4, /*ncclFloat32*/ 7, /*ncclSum*/ 0, root, c->nccl_comm, c->comm_stream);
+        if (r != 0) return nccl_fail(c, r, "ncclReduce");
+    } else {
+        // pixel maps: this rank's own (d_pixel_map) and, on the root, everybody's
+        const uint32_t mine = c->pixel_map_len;
+        if (c->d_snapshot.n < std::max(mine, 1u)) RPT_CUDA(c, c->d_snapshot.alloc(std::max(mine, 1u)));
+        if (is_root && (c->gather_maps.size() != (size_t)c->nccl_nranks || c->gather_w != c->config.width || c->gather_h != c->config.height)) {
+            c->drop_gather_maps();
+            c->gather_maps.resize((size_t)c->nccl_nranks);
+            size_t total = 0;
+            for (int r = 0; r < c->nccl_nranks; ++r) {
+                uint32_t count = 0;
+                rpt_tile_partition_pixels(c->config.width, c->config.height, (uint32_t)r, c->tile_count, nullptr, &count);
+                std::vector<uint32_t> map(count);
+                if (count) rpt_tile_partition_pixels(c->config.width, c->config.height, (uint32_t)r, c->tile_count, map.data(), &count);
+                c->gather_maps[(size_t)r].count = count;
+                if (count) RPT_CUDA(c, c->gather_maps[(size_t)r].map.upload(map.data(), count, c->stream));
+                RPT_CUDA(c, cudaStreamSynchronize(c->stream));  // `map` dies here
+                total += count;
+            }
+            if (total != npix) return c->fail(RPT_ERR_CUDA, "tile partitions cover %zu of %u pixels", total, npix);
+            RPT_CUDA(c, c->d_gather.alloc(npix));
+            c->gather_w = c->config.width; c->gather_h = c->config.height;
+        }
+        launch_pack_pixels(c->d_output.p, c->d_pixel_map.p, c->d_snapshot.p, mine, c->sm_count, c->stream);
+        c->kernel_launches++;
+        RPT_CUDA(c, cudaGetLastError());
+        RPT_CUDA(c, cudaEventRecord(c->ev_snapshot, c->stream));
+        RPT_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_snapshot, 0));
+        int r = g_nccl.GroupStart();
+        if (r != 0) return nccl_fail(c, r, "ncclGroupStart");
+        if (!is_root) {
+            if (mine) r = g_nccl.Send(c->d_snapshot.p, (size_t)mine * 4, 7, root, c->nccl_comm, c->comm_stream);
+        } else {
+            size_t offset = 0;
+            for (int k = 0; k < c->nccl_nranks && r == 0; ++k) {
+                const uint32_t count = c->gather_maps[(size_t)k].count;
+                if (k != root && count) r = g_nccl.Recv(c->d_gather.p + offset, (size_t)count * 4, 7, k, c->nccl_comm, c->comm_stream);
+                offset += count;
+            }
+        }
+        const int e = g_nccl.GroupEnd();
+        if (r != 0 || e != 0) return nccl_fail(c, r != 0 ? r : e, "tile gather (ncclSend / ncclRecv)");
+        if (is_root) {
+            size_t offset = 0;
+            for (int k = 0; k < c->nccl_nranks; ++k) {
+                const rpt_context::RankTiles& t = c->gather_maps[(size_t)k];
+                launch_unpack_pixels(k == root ? c->d_snapshot.p : c->d_gather.p + offset, t.map.p, c->d_combined.p, t.count, c->sm_count, c->comm_stream);
+                c->kernel_launches++;
+                offset += t.count;
+            }
+            RPT_CUDA(c, cudaGetLastError());
+        }
+    }
+    RPT_CUDA(c, cudaEventRecord(c->ev_combined, c->comm_stream));
+    if (is_root) c->combined_valid = true;
     return RPT_OK;
 }
 
@@ -1047,6 +1237,7 @@ extern "C" int rpt_comm_destroy(rpt_context* c) {
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
     if (c->nccl_comm) {
         bind_device(c);
+        if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
         cudaStreamSynchronize(c->stream);
         g_nccl.CommDestroy(c->nccl_comm);
         c->nccl_comm = nullptr;

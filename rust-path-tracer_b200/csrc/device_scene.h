@@ -105,7 +105,7 @@ struct WaveState {
     uint32_t* q_shaded;  // per hit: slot | kShadedNoNext | kShadedShadow (wf_shade_kernel -> wf_compact_shaded_kernel)
     uint32_t* q_shadow;  // indices of the shadow rays to trace
     WaveCtl* ctl;
-    unsigned long long* counters;  // [0] paths, [1] nearest rays, [2] any rays
+    unsigned long long* counters;  // [0] paths, [1] nearest rays, [2] any rays, [3] surface hits shaded; diagnostic build: [4] node visits / [5] triangle tests of nearest rays, [6] / [7] of any rays
 };
 
 constexpr uint32_t kShadedShadow = 0x80000000u, kShadedNoNext = 0x40000000u, kShadedSlotMask = 0x3FFFFFFFu;  // waves hold < 2^30 slots
@@ -124,6 +124,7 @@ struct WaveLaunch {
     uint2* stack_overflow;    // global overflow area of the traversal stacks (trace_stack_overflow_entries); null when the tree fits the shared slab
     bool defer_extend, defer_shadow;  // trace with deferred triangle tests (wf_trace_deferred_kernel)
     int flush_at, flush_keep;         // triangle rounds start at / go on while this many lanes hold a queued triangle
+    bool trace_statistics;            // diagnostic build of the trace kernels: count node visits / triangle tests
 };
 
 size_t trace_stack_overflow_entries(int grid_blocks);  // uint2 entries the trace kernels need for a grid of that many blocks
@@ -137,6 +138,8 @@ void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld&
 void launch_wf_compact_shaded(const WaveLaunch& l, const WaveState& s, int out_queue);
 void launch_wf_miss(const WaveLaunch& l, const FrameParams& f, const WaveState& s);
 void launch_wf_accumulate(const WaveLaunch& l, const WaveState& s, const WaveDesc& d, uint2* rng, float4* output);
+void launch_pack_pixels(const float4* frame, const uint32_t* map, float4* packed, uint32_t n, int grid, cudaStream_t stream);
+void launch_unpack_pixels(const float4* packed, const uint32_t* map, float4* frame, uint32_t n, int grid, cudaStream_t stream);
 void launch_normalize(const float4* output, float* rgb, uint32_t npixels, float samples, cudaStream_t stream);  // display_nofma.cu
 void launch_display(const float4* output, float* rgb, uint32_t npixels, float samples, uint32_t tonemap_op, cudaStream_t stream);
 void launch_display_rgba8(const float4* output, uint32_t* rgba8, uint32_t npixels, float samples, uint32_t tonemap_op, bool srgb, cudaStream_t stream);

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f,
     const LightRecord* const lights = LIGHTS_IN_SMEM ? reinterpret_cast<const LightRecord*>(sm_lights) : w.lights;
     const LightBin* const light_bins = LIGHTS_IN_SMEM ? reinterpret_cast<const LightBin*>(sm_lights + w.nlights * (uint32_t)(sizeof(LightRecord) / 4)) : w.light_bins;
     const uint32_t n = s.ctl->n_hit;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.counters + 3, (unsigned long long)n);  // surface hits shaded
     const bool nee = f.nee != RPT_NEE_NONE;
     const bool last_bounce = bounce + 1u >= f.max_bounces;
     // The first two levels of the dependent load chain (q_hit[i] -> slot -> hit[slot]) are software-pipelined two
@@ -231,6 +232,15 @@ __global__ void __launch_bounds__(256) wf_accumulate_kernel(WaveState s, WaveDes
     }
 }
 
+// Multi-GPU tile combine: the pixels a rank owns, packed in pixel-map order for the wire, and their scatter into the
+// combined frame on the root (every pixel belongs to exactly one rank, so the frame is written exactly once).
+__global__ void __launch_bounds__(256) pack_pixels_kernel(const float4* __restrict__ frame, const uint32_t* __restrict__ map, float4* __restrict__ packed, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) packed[i] = frame[__ldg(map + i)];
+}
+__global__ void __launch_bounds__(256) unpack_pixels_kernel(const float4* __restrict__ packed, const uint32_t* __restrict__ map, float4* __restrict__ frame, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) frame[__ldg(map + i)] = packed[i];
+}
+
 // Clears the per-bounce queue lengths (whole = true also clears the current extend queue).
 __global__ void wf_reset_kernel(WaveState s, int next_queue, bool whole) {
     if (threadIdx.x == 0) {
@@ -255,6 +265,12 @@ void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld&
     else if (tangents) RPT_SHADE(false, false, true);   // (more than 64 materials: everything from global memory)
     else RPT_SHADE(false, false, false);
 #undef RPT_SHADE
+}
+void launch_pack_pixels(const float4* frame, const uint32_t* map, float4* packed, uint32_t n, int grid, cudaStream_t stream) {
+    if (n) pack_pixels_kernel<<<grid * 8, 256, 0, stream>>>(frame, map, packed, n);
+}
+void launch_unpack_pixels(const float4* packed, const uint32_t* map, float4* frame, uint32_t n, int grid, cudaStream_t stream) {
+    if (n) unpack_pixels_kernel<<<grid * 8, 256, 0, stream>>>(packed, map, frame, n);
 }
 void launch_wf_reset(const WaveLaunch& l, const WaveState& s, int next_queue, bool whole) { wf_reset_kernel<<<1, 32, 0, l.stream>>>(s, next_queue, whole); }
 void launch_wf_miss_procedural(const WaveLaunch& l, const FrameParams& f, const WaveState& s) {

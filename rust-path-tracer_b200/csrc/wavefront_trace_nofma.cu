@@ -77,7 +77,10 @@ __global__ void __launch_bounds__(256) wf_generate_kernel(FrameParams f, WaveSta
 
 constexpr uint32_t kMissRecord = 0xFFFFFFFFu;  // hit[].y of a ray that hit nothing (triangle indices are < 2^31)
 
-template <bool NEAREST, bool DEEP>
+// STATS = true is the diagnostic build (rpt_set_trace_statistics): it also counts the node visits and ray/triangle
+// tests of the launch — the kernel's work in ITS OWN layout (80 B per node, 48 B per triangle record) — into
+// counters[4..7]; the product launches STATS = false.
+template <bool NEAREST, bool DEEP, bool STATS>
 __global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
                                                                int refill_below, uint2* stack_overflow) {
     __shared__ uint2 slabs[kTraceWarps][kWideStackShared][32];
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh,
     uint32_t item = 0;       // path slot (NEAREST) / index of the shadow ray (ANY)
     bool busy = false;       // this lane holds an unfinished ray
     bool exhausted = false;  // the cursor ran past the end of the queue (warp-uniform)
+    uint32_t stat_visits = 0, stat_tests = 0;
 
     for (;;) {
         // ---- converged: refill idle lanes -------------------------------------------------------
@@ -136,9 +140,14 @@ __global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh,
         // ---- traverse until the ray ends or the warp wants a refill ---------------------------
         while (busy) {
             bool finished = false;
-            if (c.has_nodes()) c.visit_node(bvh, st);  // (only a non-finite ray starts without nodes)
-            while (c.has_triangles())
+            if (c.has_nodes()) {  // (only a non-finite ray starts without nodes)
+                c.visit_node(bvh, st);
+                if (STATS) ++stat_visits;
+            }
+            while (c.has_triangles()) {
+                if (STATS) ++stat_tests;
                 if (c.test_triangle(bvh)) { finished = true; break; }
+            }
             if (!c.has_nodes()) finished = true;
             if (finished) {
                 busy = false;
@@ -154,6 +163,16 @@ __global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh,
                 break;
             }
             if (!exhausted && __popc(__activemask()) < refill_below) break;
+        }
+    }
+    if (STATS) {
+        for (int d = 16; d > 0; d >>= 1) {
+            stat_visits += __shfl_xor_sync(0xFFFFFFFFu, stat_visits, d);
+            stat_tests += __shfl_xor_sync(0xFFFFFFFFu, stat_tests, d);
+        }
+        if (lane == 0u) {
+            atomicAdd(s.counters + (NEAREST ? 4 : 6), (unsigned long long)stat_visits);
+            atomicAdd(s.counters + (NEAREST ? 5 : 7), (unsigned long long)stat_tests);
         }
     }
 }
@@ -408,10 +427,14 @@ void launch_wf_extend(const WaveLaunch& l, const WideScene& bvh, const WaveState
         wf_trace_deferred_kernel<true, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.flush_at, l.flush_keep, l.stack_overflow);
     else if (l.defer_extend)
         wf_trace_deferred_kernel<true, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.flush_at, l.flush_keep, nullptr);
+    else if (l.trace_statistics && l.stack_overflow)
+        wf_trace_kernel<true, true, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.stack_overflow);
+    else if (l.trace_statistics)
+        wf_trace_kernel<true, false, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, nullptr);
     else if (l.stack_overflow)
-        wf_trace_kernel<true, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.stack_overflow);
+        wf_trace_kernel<true, true, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, l.stack_overflow);
     else
-        wf_trace_kernel<true, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, nullptr);
+        wf_trace_kernel<true, false, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, in_queue, identity_queue, n_identity, l.refill_below, nullptr);
     wf_compact_kernel<<<l.grid * 8, kCompactBlock, 0, l.stream>>>(s, in_queue, identity_queue, n_identity);
 }
 void launch_wf_compact_shaded(const WaveLaunch& l, const WaveState& s, int out_queue) {
@@ -422,10 +445,14 @@ void launch_wf_shadow(const WaveLaunch& l, const WideScene& bvh, const WaveState
         wf_trace_deferred_kernel<false, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.flush_at, l.flush_keep, l.stack_overflow);
     else if (l.defer_shadow)
         wf_trace_deferred_kernel<false, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.flush_at, l.flush_keep, nullptr);
+    else if (l.trace_statistics && l.stack_overflow)
+        wf_trace_kernel<false, true, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.stack_overflow);
+    else if (l.trace_statistics)
+        wf_trace_kernel<false, false, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, nullptr);
     else if (l.stack_overflow)
-        wf_trace_kernel<false, true><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.stack_overflow);
+        wf_trace_kernel<false, true, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, l.stack_overflow);
     else
-        wf_trace_kernel<false, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, nullptr);
+        wf_trace_kernel<false, false, false><<<l.grid * l.trace_blocks_per_sm, kTraceBlock, 0, l.stream>>>(bvh, s, 0, false, 0u, l.refill_below, nullptr);
 }
 void launch_wf_export_primary(const WaveLaunch& l, const WideScene& bvh, const WaveState& s, const WaveDesc& d, uint32_t* ids) {
     wf_export_primary_kernel<<<(d.npix + 255) / 256, 256, 0, l.stream>>>(bvh, s, d, ids);

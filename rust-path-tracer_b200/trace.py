@@ -162,6 +162,29 @@ class Renderer:
         self._call("rpt_get_device_ms", C.byref(ms))
         return ms.value
 
+    def timer_start(self):
+        self._call("rpt_timer_start")
+
+    def timer_stop(self) -> float:
+        """Device milliseconds since timer_start (enqueues and the combine); waits for that work."""
+        ms = C.c_float(0)
+        self._call("rpt_timer_stop", C.byref(ms))
+        return ms.value
+
+    def sm_count(self) -> int:
+        n = C.c_int(0)
+        self._call("rpt_get_sm_count", C.byref(n))
+        return n.value
+
+    def set_trace_statistics(self, enable: bool):
+        self._call("rpt_set_trace_statistics", C.c_int(int(enable)))
+
+    def trace_statistics(self) -> dict:
+        """Node visits / triangle tests counted by the diagnostic build of the trace kernels since reset_counters."""
+        t = capi.TraceStatistics()
+        self._call("rpt_get_trace_statistics", C.byref(t))
+        return {name: getattr(t, name) for name, _ in capi.TraceStatistics._fields_}
+
     def set_stage_timing(self, enable: bool):
         self._call("rpt_set_stage_timing", C.c_int(int(enable)))
 

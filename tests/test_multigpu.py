@@ -45,8 +45,14 @@ def test_nccl_reduce_matches_single_gpu(mode):
                     count = spp
                 r.comm_init(uid, rank, n)
                 r.enqueue(count)
+                own = None
+                if rank != 0:
+                    own = r.read_output()
                 r.comm_reduce_output(0)
+                r.comm_reduce_output(0)  # the combine modifies no accumulator: combining twice gives the same frame
                 results[rank] = r.read_output()
+                if rank != 0:  # only the root holds a combined frame; the others still read their own accumulator
+                    np.testing.assert_array_equal(results[rank], own)
                 r.comm_destroy()
         except Exception as e:  # noqa: BLE001
             errors.append(e)
