@@ -10,6 +10,9 @@
  *   rpt_make_rng_seeds          <- blue-noise / uniform seed tables, src/trace.rs:149-160, 245-256
  *   rpt_atlas_rects / rpt_atlas_pack / rpt_decode_albedo_gamma
  *                               <- pack_textures, src/atlas.rs:26-92, and the albedo decode of src/asset.rs:140-147
+ *   rpt_decode_hdr / rpt_sky_texels
+ *                               <- load_dynamic_image's .hdr branch and the GPU / CPU texel conventions of the sky image,
+ *                                  src/asset.rs:238-273
  *   rpt_tile_partition_pixels   <- (new) the tile split used by rpt_set_tile_partition
  *   rpt_camera_matrix           <- Mat3::from_rotation_y(ry) * Mat3::from_rotation_x(rx),
  *                                  kernels/src/lib.rs:50 (host libm keeps primary rays bit-exact)
@@ -58,6 +61,14 @@ int rpt_atlas_pack(const uint8_t* const* textures_rgba8, const uint32_t* widths,
                    uint32_t atlas_w, uint32_t atlas_h, uint8_t* atlas_rgba8_out, float* sts_out);
 /* `((p / 255).powf(2.2) * 255) as u8` on RGB, alpha -> 255 (albedo textures, before packing). */
 int rpt_decode_albedo_gamma(const uint8_t* rgba8_in, size_t npixels, uint8_t* rgba8_out);
+
+/* Radiance .hdr (RGBE) file -> packed RGB float (src/asset.rs:238-254; `image` 0.24 HdrDecoder semantics: RGBE value
+ * c * 2^(e-136), e == 0 -> 0; "-Y h +X w" orientation only).  rgb_out may be NULL to query the size. */
+int rpt_decode_hdr(const uint8_t* bytes, size_t nbytes, float* rgb_out, uint32_t* width_out, uint32_t* height_out);
+/* Sky texels as the tracing loop reads them, float[4] per texel.  cpu_path_rgb8 == 0: (r, g, b, 1), the GPU path's
+ * Rgba32Float upload (src/asset.rs:257-264); != 0: the CPU path's `into_rgb8()` quantisation, every channel clamped to
+ * [0, 1], rounded to 8 bits and divided by 255 (src/asset.rs:266-273). */
+int rpt_sky_texels(const float* rgb, uint32_t width, uint32_t height, int cpu_path_rgb8, float* rgba_out);
 
 /* Multi-GPU tile split: pixel indices (row-major y*width+x) of the 32x32 tiles t
  * with t % tile_count == tile_rank, tile by tile.  pixels_out may be NULL to query the count. */

@@ -22,7 +22,7 @@ TONEMAPS = ["none", "reinhard", "aces_narkowicz", "aces_narkowicz_overexposed", 
 
 # every symbol the headers declare (tests check the library exports each of them)
 HOST_SYMBOLS = ["rpt_build_bvh", "rpt_build_light_pick_table", "rpt_pack_per_vertex", "rpt_make_rng_seeds", "rpt_camera_matrix",
-                "rpt_tile_partition_pixels", "rpt_atlas_rects", "rpt_atlas_pack", "rpt_decode_albedo_gamma"]
+                "rpt_tile_partition_pixels", "rpt_atlas_rects", "rpt_atlas_pack", "rpt_decode_albedo_gamma", "rpt_decode_hdr", "rpt_sky_texels"]
 DEVICE_SYMBOLS = [
     "rpt_create", "rpt_destroy", "rpt_last_error", "rpt_set_pipeline", "rpt_set_wave_slots", "rpt_upload_world",
     "rpt_set_config", "rpt_write_rng", "rpt_read_rng", "rpt_write_output", "rpt_set_tile_partition", "rpt_enqueue",

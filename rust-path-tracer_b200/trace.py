@@ -244,13 +244,33 @@ def setup_trace(width: int, height: int, samples: int) -> TracingState:
     return state
 
 
-def load_skybox(path: str | None) -> np.ndarray | None:
-    """`load_dynamic_image` + `dynamic_image_to_gpu_image::<Rgba32Float>` (src/asset.rs:238-264):
-    .npy (H,W,3|4 float32) or any PIL-readable image; returns (H,W,4) float32 or None."""
+def decode_hdr(data: bytes) -> np.ndarray | None:
+    """Radiance .hdr bytes -> (H, W, 3) float32 (csrc/image_io.cpp, `HdrDecoder` semantics); None if malformed."""
+    lib = capi.lib()
+    buf = np.frombuffer(data, np.uint8)
+    w, h = C.c_uint32(0), C.c_uint32(0)
+    if lib.rpt_decode_hdr(capi.ptr(buf), C.c_size_t(len(buf)), None, C.byref(w), C.byref(h)) != capi.OK:
+        return None
+    out = np.empty((h.value, w.value, 3), np.float32)
+    if lib.rpt_decode_hdr(capi.ptr(buf), C.c_size_t(len(buf)), capi.ptr(out), C.byref(w), C.byref(h)) != capi.OK:
+        return None
+    return out
+
+
+def load_skybox(path: str | None, cpu_path_rgb8: bool = False) -> np.ndarray | None:
+    """`load_dynamic_image` + the texel conversion of the sky image (src/asset.rs:238-273): a Radiance .hdr file
+    (decoded natively), a .npy array (H,W,3|4 float32) or any PIL-readable 8-bit image.  Returns (H,W,4) float32 texels —
+    as the GPU path uploads them (Rgba32Float, `dynamic_image_to_gpu_image`), or with `cpu_path_rgb8` as the CPU path
+    reads them (`dynamic_image_to_cpu_buffer`: clamped to [0,1] and quantised to 8 bits) — or None on failure."""
     if path is None:
         return None
     try:
-        if path.endswith(".npy"):
+        if path.endswith(".hdr"):
+            with open(path, "rb") as f:
+                img = decode_hdr(f.read())
+            if img is None:
+                return None
+        elif path.endswith(".npy"):
             img = np.load(path).astype(np.float32)
         else:
             from PIL import Image
@@ -260,9 +280,11 @@ def load_skybox(path: str | None) -> np.ndarray | None:
         return None
     if img.ndim != 3 or img.shape[2] not in (3, 4):
         return None
-    if img.shape[2] == 3:
-        img = np.concatenate([img, np.ones(img.shape[:2] + (1,), np.float32)], axis=2)
-    return np.ascontiguousarray(img, np.float32)
+    rgb = np.ascontiguousarray(img[..., :3], np.float32)
+    out = np.empty(rgb.shape[:2] + (4,), np.float32)
+    capi.check(capi.lib().rpt_sky_texels(capi.ptr(rgb), C.c_uint32(rgb.shape[1]), C.c_uint32(rgb.shape[0]), C.c_int(int(cpu_path_rgb8)), capi.ptr(out)),
+               "rpt_sky_texels")
+    return out
 
 
 def trace_gpu(scene_path: str, skybox_path: str | None, state: TracingState, device: int = 0,
