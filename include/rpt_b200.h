@@ -98,12 +98,30 @@ int rpt_host_free(void* ptr);
 /* ---- run ------------------------------------------------------------------------------- */
 int rpt_enqueue(rpt_context* ctx, uint32_t n_samples); /* asynchronous */
 int rpt_sync(rpt_context* ctx);                        /* FW.poll_blocking() */
+/* rpt_enqueue that can be cut short like the reference's dispatch loop, which looks at `interacting | dirty` and
+ * `running` after every sample (src/trace.rs:182-193): after every `poll_samples` samples (0 = 1) the batch is drained and
+ * *stop_flag — host memory another thread may write, or NULL — is read; non-zero ends the batch.  *finished_out =
+ * samples rendered (a multiple of poll_samples unless the batch ended).  Returns with the stream idle. */
+int rpt_enqueue_interruptible(rpt_context* ctx, uint32_t n_samples, const volatile uint32_t* stop_flag, uint32_t poll_samples,
+                              uint32_t* finished_out);
 
 /* ---- readback -------------------------------------------------------------------------- */
 /* Raw accumulator, float[4] per pixel (sum rgb, w = sample count). Implies rpt_sync. */
 int rpt_read_output(rpt_context* ctx, float* rgba, size_t npixels);
 /* Packed RGB `output.xyz / samples` normalised on the device (src/trace.rs:199-204). */
 int rpt_read_framebuffer(rpt_context* ctx, float* rgb, size_t npixels, float samples);
+/* The same without the wait: normalise on the render stream, copy on a copy stream into `rgb` (page-locked memory:
+ * rpt_host_alloc; it must stay valid until rpt_readback_wait), two frames in flight at most.  The next rpt_enqueue
+ * overlaps the copy; rpt_readback_wait (or rpt_sync) returns when `rgb` holds the frame. */
+int rpt_read_framebuffer_async(rpt_context* ctx, float* rgb, size_t npixels, float samples);
+int rpt_readback_wait(rpt_context* ctx);
+/* Post-normalise hook — the slot of the reference's denoiser (src/trace.rs:207-210: `denoise_image(w, h, &mut
+ * image_buffer)` between the division by the sample count and the hand-over to the display): called by
+ * rpt_read_framebuffer[_async] after the frame has been normalised on the device and before it is copied out, with the
+ * DEVICE pointer of the packed RGB frame (width * height * 3 floats, modifiable in place) and the cudaStream_t the
+ * library works on — the hook must enqueue its work on that stream (or synchronise itself).  NULL removes it. */
+typedef void (*rpt_frame_hook)(float* rgb_device, uint32_t width, uint32_t height, void* cuda_stream, void* user);
+int rpt_set_frame_hook(rpt_context* ctx, rpt_frame_hook hook, void* user);
 /* Display resolve on the device — the fragment stage of src/resources/render.wgsl:150-185 (fs_main):
  * rgb = tonemap(output.xyz / samples), row-major, top-left origin.  `tonemap` is the reference's `Tonemapping`
  * enum value (src/app.rs:20-28): 0 none, 1 Reinhard, 2 ACES Narkowicz (input x 0.6), 3 ACES Narkowicz

@@ -26,7 +26,7 @@ HOST_SYMBOLS = ["rpt_build_bvh", "rpt_build_light_pick_table", "rpt_pack_per_ver
 DEVICE_SYMBOLS = [
     "rpt_create", "rpt_destroy", "rpt_last_error", "rpt_set_pipeline", "rpt_set_wave_slots", "rpt_upload_world",
     "rpt_set_config", "rpt_write_rng", "rpt_read_rng", "rpt_write_output", "rpt_set_tile_partition", "rpt_enqueue",
-    "rpt_sync", "rpt_read_output", "rpt_read_framebuffer", "rpt_read_display", "rpt_read_display_rgba8", "rpt_read_primary_ids", "rpt_get_counters",
+    "rpt_sync", "rpt_enqueue_interruptible", "rpt_read_output", "rpt_read_framebuffer", "rpt_read_framebuffer_async", "rpt_readback_wait", "rpt_set_frame_hook", "rpt_read_display", "rpt_read_display_rgba8", "rpt_read_primary_ids", "rpt_get_counters",
     "rpt_reset_counters", "rpt_get_device_ms", "rpt_set_stage_timing", "rpt_get_stage_timing", "rpt_set_trace_statistics", "rpt_get_trace_statistics", "rpt_get_sm_count", "rpt_timer_start", "rpt_timer_stop", "rpt_comm_unique_id", "rpt_comm_init", "rpt_comm_reduce_output",
     "rpt_comm_destroy", "rpt_host_alloc", "rpt_host_free",
 ]
@@ -88,6 +88,8 @@ STAGES = ["generate", "extend", "miss", "shade", "shadow", "accumulate", "megake
 class StageTiming(C.Structure):
     _fields_ = [("ms", C.c_float * 8), ("launches", C.c_uint64 * 8)]
 
+
+FRAME_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p)  # rpt_frame_hook
 
 BVH_NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("triangle_count", "<u4"), ("aabb_max", "<f4", 3), ("left_or_first", "<u4")])
 LIGHT_DTYPE = np.dtype(

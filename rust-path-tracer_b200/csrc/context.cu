@@ -211,6 +211,15 @@ struct rpt_context {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
     float device_ms = 0.0f;
     cudaEvent_t region_start = nullptr, region_stop = nullptr;  // rpt_timer_start / rpt_timer_stop
+    // asynchronous readback (rpt_read_framebuffer_async): two device frames, filled on the render stream and copied out
+    // on `copy_stream`, so the next batch renders while the previous frame crosses PCIe
+    cudaStream_t copy_stream = nullptr;
+    DevBuf<float> d_rgb_async[2];
+    cudaEvent_t ev_frame_ready[2] = {nullptr, nullptr}, ev_frame_copied[2] = {nullptr, nullptr};
+    int async_next = 0;
+    // post-normalise hook (the reference's denoiser slot, src/trace.rs:207-210)
+    rpt_frame_hook frame_hook = nullptr;
+    void* frame_hook_user = nullptr;
 
     void* nccl_comm = nullptr;
     int nccl_rank = 0, nccl_nranks = 1;
@@ -549,6 +558,11 @@ extern "C" int rpt_destroy(rpt_context* c) {
     c->d_snapshot.release(); c->d_combined.release(); c->d_gather.release();
     for (auto& ev : c->timed) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (c->region_start) { cudaEventDestroy(c->region_start); cudaEventDestroy(c->region_stop); }
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(c->ev_frame_ready[k]); cudaEventDestroy(c->ev_frame_copied[k]); c->d_rgb_async[k].release(); }
+        cudaStreamDestroy(c->copy_stream);
+    }
     c->drain_stage_events();
     for (auto* b : {&c->w_ray_o, &c->w_ray_d, &c->w_thr, &c->w_rad, &c->w_sh_o, &c->w_sh_d, &c->w_sh_c, &c->d_tri_pos,
                     &c->d_tri_shade, &c->d_sky, &c->d_output})
@@ -788,6 +802,8 @@ extern "C" int rpt_set_config(rpt_context* c, const RptTracingConfig* cfg) {
         RPT_CUDA(c, c->d_rng.alloc(n));
         RPT_CUDA(c, c->d_output.alloc(n));
         RPT_CUDA(c, cudaMemsetAsync(c->d_output.p, 0, n * sizeof(float4), c->stream));
+        if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+        c->d_rgb_async[0].release(); c->d_rgb_async[1].release();
         c->d_rgb.release();
         c->d_rgba8.release();
         c->d_ids.release();
@@ -909,11 +925,32 @@ extern "C" int rpt_enqueue(rpt_context* c, uint32_t n_samples) {
     return status;
 }
 
+// The reference's dispatch loop looks at its control flags after EVERY sample (src/trace.rs:182-193) and leaves the
+// batch early when the camera moves or the render is stopped.  Here the batch is cut into groups of `poll_samples`
+// samples; after each group the stream is drained and `*stop_flag` (host memory another thread may set) is read.
+extern "C" int rpt_enqueue_interruptible(rpt_context* c, uint32_t n_samples, const volatile uint32_t* stop_flag, uint32_t poll_samples,
+                                         uint32_t* finished_out) {
+    if (!c || !finished_out) return RPT_ERR_INVALID_ARGUMENT;
+    *finished_out = 0;
+    if (poll_samples == 0) poll_samples = 1;
+    for (uint32_t done = 0; done < n_samples;) {
+        const uint32_t group = std::min(poll_samples, n_samples - done);
+        RPT_TRY(rpt_enqueue(c, group));
+        RPT_CUDA(c, cudaStreamSynchronize(c->stream));
+        done += group;
+        *finished_out = done;
+        if (stop_flag && *stop_flag != 0u) break;
+    }
+    return RPT_OK;
+}
+
 extern "C" int rpt_sync(rpt_context* c) {
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
     RPT_TRY(bind_device(c));
     if (c->comm_stream) RPT_CUDA(c, cudaStreamSynchronize(c->comm_stream));
-    return c->cuda(cudaStreamSynchronize(c->stream), "rpt_sync");
+    RPT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) RPT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    return RPT_OK;
 }
 
 // ============================================================================ readback
@@ -935,8 +972,52 @@ extern "C" int rpt_read_framebuffer(rpt_context* c, float* rgb, size_t npixels, 
     launch_normalize(c->frame_for_read(), c->d_rgb.p, (uint32_t)npixels, samples, c->stream);
     c->kernel_launches++;
     RPT_CUDA(c, cudaGetLastError());
+    if (c->frame_hook) c->frame_hook(c->d_rgb.p, c->config.width, c->config.height, c->stream, c->frame_hook_user);
     RPT_CUDA(c, cudaMemcpyAsync(rgb, c->d_rgb.p, npixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     return c->cuda(cudaStreamSynchronize(c->stream), "rpt_read_framebuffer");
+}
+
+extern "C" int rpt_set_frame_hook(rpt_context* c, rpt_frame_hook hook, void* user) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    c->frame_hook = hook;
+    c->frame_hook_user = user;
+    return RPT_OK;
+}
+
+// rpt_read_framebuffer without the wait: the frame is normalised on the render stream into one of two device
+// buffers and copied to `rgb` (page-locked: rpt_host_alloc) on a copy stream; the caller goes on enqueueing and calls
+// rpt_readback_wait before it reads `rgb`.
+extern "C" int rpt_read_framebuffer_async(rpt_context* c, float* rgb, size_t npixels, float samples) {
+    if (!c || !rgb) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->has_config) return c->fail(RPT_ERR_NOT_READY, "rpt_read_framebuffer_async before rpt_set_config");
+    if (npixels != c->npixels()) return c->fail(RPT_ERR_SIZE_MISMATCH, "frame has %u pixels, caller asked for %zu", c->npixels(), npixels);
+    RPT_TRY(bind_device(c));
+    if (!c->copy_stream) {
+        RPT_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            RPT_CUDA(c, cudaEventCreateWithFlags(&c->ev_frame_ready[k], cudaEventDisableTiming));
+            RPT_CUDA(c, cudaEventCreateWithFlags(&c->ev_frame_copied[k], cudaEventDisableTiming));
+        }
+    }
+    const int k = c->async_next;
+    c->async_next ^= 1;
+    if (c->d_rgb_async[k].n != npixels * 3) RPT_CUDA(c, c->d_rgb_async[k].alloc(npixels * 3));
+    RPT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_frame_copied[k], 0));  // the copy that last used this buffer
+    launch_normalize(c->frame_for_read(), c->d_rgb_async[k].p, (uint32_t)npixels, samples, c->stream);
+    c->kernel_launches++;
+    RPT_CUDA(c, cudaGetLastError());
+    if (c->frame_hook) c->frame_hook(c->d_rgb_async[k].p, c->config.width, c->config.height, c->stream, c->frame_hook_user);
+    RPT_CUDA(c, cudaEventRecord(c->ev_frame_ready[k], c->stream));
+    RPT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_frame_ready[k], 0));
+    RPT_CUDA(c, cudaMemcpyAsync(rgb, c->d_rgb_async[k].p, npixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+    return c->cuda(cudaEventRecord(c->ev_frame_copied[k], c->copy_stream), "rpt_read_framebuffer_async");
+}
+
+extern "C" int rpt_readback_wait(rpt_context* c) {
+    if (!c) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->copy_stream) return RPT_OK;
+    RPT_TRY(bind_device(c));
+    return c->cuda(cudaStreamSynchronize(c->copy_stream), "rpt_readback_wait");
 }
 
 extern "C" int rpt_read_display(rpt_context* c, float* rgb, size_t npixels, float samples, uint32_t tonemap) {

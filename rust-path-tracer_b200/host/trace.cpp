@@ -54,6 +54,14 @@ bool load_skybox(const char* path, std::vector<float>& texels, uint32_t& w, uint
     std::vector<uint8_t> buf;
     size_t off;
     std::string hdr;
+    const std::string name(path);
+    if (name.size() > 4 && name.compare(name.size() - 4, 4, ".hdr") == 0) {  // load_dynamic_image's HDR branch, src/asset.rs:240-253
+        if (!read_file(path, buf) || rpt_decode_hdr(buf.data(), buf.size(), nullptr, &w, &h) != RPT_OK) return false;
+        std::vector<float> rgb((size_t)w * h * 3);
+        if (rpt_decode_hdr(buf.data(), buf.size(), rgb.data(), &w, &h) != RPT_OK) return false;
+        texels.resize((size_t)w * h * 4);
+        return rpt_sky_texels(rgb.data(), w, h, /*cpu_path_rgb8=*/0, texels.data()) == RPT_OK;  // Rgba32Float upload, src/asset.rs:257-264
+    }
     if (!read_file(path, buf) || !npy_payload(buf, off, hdr) || hdr.find("<f4") == std::string::npos) return false;
     unsigned long sh, sw, sc;
     const size_t p = hdr.find("'shape': (");
@@ -189,10 +197,26 @@ int trace_gpu(const std::string& scene_path, const char* skybox_path, std::share
     };
     while (state->running.load(std::memory_order_relaxed)) {
         const uint32_t sync_rate = state->sync_rate.load(std::memory_order_relaxed);
-        const bool flush = state->interacting.load(std::memory_order_relaxed) || state->dirty.load(std::memory_order_relaxed);
-        const uint32_t batch = flush ? 1u : sync_rate;  // the reference breaks out of its dispatch loop after one sample when flushing
-        if ((rc = rpt_enqueue(ctx, batch)) != RPT_OK) return fail_loop("rpt_enqueue");
-        if ((rc = rpt_sync(ctx)) != RPT_OK) return fail_loop("rpt_sync");
+        // The reference reads its control flags after EVERY sample of a batch (src/trace.rs:182-193): it leaves the
+        // batch when `interacting | dirty` is set and abandons it when `running` is cleared.  Same here, sample by
+        // sample, while somebody may be steering (a frame that already flushes takes one sample, as in the reference);
+        // an undisturbed batch is one uninterrupted enqueue.
+        bool flush = state->interacting.load(std::memory_order_relaxed) || state->dirty.load(std::memory_order_relaxed);
+        uint32_t batch = 0;
+        if (flush || state->poll_every_sample.load(std::memory_order_relaxed)) {
+            while (batch < sync_rate) {
+                if ((rc = rpt_enqueue(ctx, 1)) != RPT_OK) return fail_loop("rpt_enqueue");
+                if ((rc = rpt_sync(ctx)) != RPT_OK) return fail_loop("rpt_sync");
+                ++batch;
+                flush |= state->interacting.load(std::memory_order_relaxed) || state->dirty.load(std::memory_order_relaxed);
+                if (flush) break;
+                if (!state->running.load(std::memory_order_relaxed)) { rpt_host_free(image_buffer); rpt_destroy(ctx); return RPT_OK; }
+            }
+        } else {
+            batch = sync_rate;
+            if ((rc = rpt_enqueue(ctx, batch)) != RPT_OK) return fail_loop("rpt_enqueue");
+            if ((rc = rpt_sync(ctx)) != RPT_OK) return fail_loop("rpt_sync");
+        }
         state->samples.fetch_add(batch, std::memory_order_relaxed);
 
         const float sample_count = (float)state->samples.load(std::memory_order_relaxed);

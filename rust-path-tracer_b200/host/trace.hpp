@@ -43,6 +43,9 @@ struct TracingState {
     std::atomic<bool> use_blue_noise{true};
     std::atomic<bool> interacting{false};
     std::atomic<bool> dirty{false};
+    // (not in the reference) an interactive host sets this so that a batch is rendered sample by sample with the control
+    // flags read in between, exactly like the reference's dispatch loop; benches and tests leave it off: one enqueue per batch
+    std::atomic<bool> poll_every_sample{false};
     std::shared_mutex config_lock;  // RwLock<TracingConfig>
     RptTracingConfig config;
 

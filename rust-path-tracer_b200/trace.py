@@ -117,6 +117,25 @@ class Renderer:
     def sync(self):
         self._call("rpt_sync")
 
+    def enqueue_interruptible(self, n_samples: int, stop_flag: np.ndarray | None, poll_samples: int = 1) -> int:
+        """rpt_enqueue that reads stop_flag[0] (a uint32 array another thread may write) after every `poll_samples`
+        samples, like the reference's dispatch loop (src/trace.rs:182-193); returns the samples rendered."""
+        finished = C.c_uint32(0)
+        self._call("rpt_enqueue_interruptible", C.c_uint32(n_samples), capi.ptr(stop_flag), C.c_uint32(poll_samples), C.byref(finished))
+        return finished.value
+
+    def read_framebuffer_async(self, samples: float, out: np.ndarray):
+        """`out`: page-locked (capi.pinned_empty); valid after readback_wait()."""
+        self._call("rpt_read_framebuffer_async", capi.ptr(out), C.c_size_t(self.npixels), C.c_float(samples))
+
+    def readback_wait(self):
+        self._call("rpt_readback_wait")
+
+    def set_frame_hook(self, hook):
+        """hook(rgb_device_pointer, width, height, cuda_stream) or None — the reference's denoiser slot."""
+        self._hook = capi.FRAME_HOOK(lambda p, w, h, s, _u: hook(p, w, h, s)) if hook else C.cast(None, capi.FRAME_HOOK)
+        self._call("rpt_set_frame_hook", self._hook, None)
+
     def read_output(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:
             out = np.empty((self.npixels, 4), np.float32)
@@ -213,9 +232,13 @@ class Renderer:
 
 
 class TracingState:
-    """src/trace.rs:40-92.  Atomics become plain attributes (single-writer in this mirror)."""
+    """src/trace.rs:40-92.  Atomics become attributes; `running`, `interacting` and `dirty` also keep one word of
+    shared memory up to date (`stop_flag`: interacting | dirty | !running) that `rpt_enqueue_interruptible` polls from
+    inside a batch, the way the reference's dispatch loop reads its atomics after every sample."""
 
     def __init__(self, width: int, height: int):
+        self.stop_flag = np.zeros(1, np.uint32)
+        self._running = self._interacting = self._dirty = False
         self.config = TracingConfig.default(width, height)
         self.framebuffer = np.zeros(width * height * 3, np.float32)
         self.running = False
@@ -225,8 +248,16 @@ class TracingState:
         self.use_blue_noise = True
         self.interacting = False
         self.dirty = False
+        self.poll_samples = 1  # samples between two looks at the control flags inside a batch (the reference: 1)
         self._stop_at = None  # set by setup_trace: the watcher thread's threshold
         self.lock = threading.Lock()
+
+    def _refresh(self):
+        self.stop_flag[0] = 1 if (self._interacting or self._dirty or not self._running) else 0
+
+    running = property(lambda self: self._running, lambda self, v: (setattr(self, "_running", bool(v)), self._refresh())[1])
+    interacting = property(lambda self: self._interacting, lambda self, v: (setattr(self, "_interacting", bool(v)), self._refresh())[1])
+    dirty = property(lambda self: self._dirty, lambda self, v: (setattr(self, "_dirty", bool(v)), self._refresh())[1])
 
     def _watch(self):
         # the reference spawns a thread that clears `running` once `samples >= N`
@@ -315,11 +346,18 @@ def trace_gpu(scene_path: str, skybox_path: str | None, state: TracingState, dev
             r.write_output(init * np.float32(state.samples))
 
         while state.running:
-            # the reference leaves its dispatch loop after ONE sample while the camera moves (src/trace.rs:187-193)
+            # The reference leaves its dispatch loop as soon as a sample ends with `interacting | dirty` set, and
+            # abandons the batch when `running` is cleared (src/trace.rs:182-193).  A synchronous harness (setup_trace)
+            # has nobody to set the flags mid-batch, so it takes the whole batch in one uninterrupted enqueue.
+            if state._stop_at is not None and not (state.interacting or state.dirty):
+                r.enqueue(state.sync_rate)
+                r.sync()
+                finished = state.sync_rate
+            else:
+                finished = r.enqueue_interruptible(state.sync_rate, state.stop_flag, state.poll_samples)
+                if not state.running:
+                    return
             flush = state.interacting or state.dirty
-            finished = 1 if flush else state.sync_rate
-            r.enqueue(finished)
-            r.sync()
             state.samples += finished
             state._watch()
             with state.lock:
