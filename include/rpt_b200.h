@@ -73,6 +73,14 @@ int rpt_upload_world(rpt_context* ctx,
                      const RptLightPickEntry* lights, uint32_t nlights,
                      const uint8_t* atlas_rgba8, uint32_t atlas_w, uint32_t atlas_h,
                      const float* sky_rgba32f, uint32_t sky_w, uint32_t sky_h);
+/* Build half of SURVEY §8 f4.  rpt_upload_world with nodes == NULL and nnodes == 0 builds the traversal structure ON THE
+ * DEVICE from the vertices and triangles alone (Morton order + bottom-up fit; src/bvh.rs:257-323 is then not needed
+ * on the host): triangle ids keep referring to the caller's index buffer, results stay within the same parity bars
+ * (nearest hits do not depend on the tree), traversal is slower than over the reference's SAH tree.
+ * rpt_refit_world: the vertices moved but the topology did not — new vertex records in, triangle streams rewritten,
+ * every box refitted bottom-up on the device; `lights` optionally replaces the light-pick table (NULL keeps it and only
+ * refreshes the emitters' geometry).  After a refit the megakernel comparison arm has no reference BVH to traverse. */
+int rpt_refit_world(rpt_context* ctx, const RptPerVertexData* vertices, uint32_t nvertices, const RptLightPickEntry* lights, uint32_t nlights);
 
 /* ---- per-render state ------------------------------------------------------------------ */
 /* (Re)allocates rng/output when width*height changes; validates the RNG dimension budget. */

@@ -24,7 +24,7 @@ TONEMAPS = ["none", "reinhard", "aces_narkowicz", "aces_narkowicz_overexposed", 
 HOST_SYMBOLS = ["rpt_build_bvh", "rpt_build_light_pick_table", "rpt_pack_per_vertex", "rpt_make_rng_seeds", "rpt_camera_matrix",
                 "rpt_tile_partition_pixels", "rpt_atlas_rects", "rpt_atlas_pack", "rpt_decode_albedo_gamma", "rpt_decode_hdr", "rpt_sky_texels"]
 DEVICE_SYMBOLS = [
-    "rpt_create", "rpt_destroy", "rpt_last_error", "rpt_set_pipeline", "rpt_set_wave_slots", "rpt_upload_world",
+    "rpt_create", "rpt_destroy", "rpt_last_error", "rpt_set_pipeline", "rpt_set_wave_slots", "rpt_upload_world", "rpt_refit_world",
     "rpt_set_config", "rpt_write_rng", "rpt_read_rng", "rpt_write_output", "rpt_set_tile_partition", "rpt_enqueue",
     "rpt_sync", "rpt_enqueue_interruptible", "rpt_read_output", "rpt_read_framebuffer", "rpt_read_framebuffer_async", "rpt_readback_wait", "rpt_set_frame_hook", "rpt_read_display", "rpt_read_display_rgba8", "rpt_read_primary_ids", "rpt_get_counters",
     "rpt_reset_counters", "rpt_get_device_ms", "rpt_set_stage_timing", "rpt_get_stage_timing", "rpt_set_trace_statistics", "rpt_get_trace_statistics", "rpt_get_sm_count", "rpt_timer_start", "rpt_timer_stop", "rpt_comm_unique_id", "rpt_comm_init", "rpt_comm_reduce_output",

@@ -23,6 +23,7 @@
 
 #include "../../include/rpt_b200.h"
 #include "../../include/rpt_host.h"
+#include "device_build.h"
 #include "device_scene.h"
 #include "wide_bvh.h"
 
@@ -131,9 +132,14 @@ struct rpt_context {
     DevBuf<float4> d_sky;
     uint32_t atlas_w = 1, atlas_h = 1, sky_w = 2, sky_h = 2, nlights = 0, nmaterials = 0;
     // scene, private layouts (wavefront arm)
-    DevBuf<uint4> d_wide_nodes;
-    DevBuf<float4> d_tri_pos, d_tri_shade;
+    DeviceBuildResult tree;  // wide nodes, triangle position stream, shading records, leaf-order maps, refit scratch (owned)
     uint32_t shade_stride = kShadeStridePlain;
+    uint32_t ntriangles = 0, nvertices = 0;
+    bool device_built = false;  // the tree came from device_build_wide_bvh (no reference BVH: the megakernel arm cannot run)
+    // host copies a refit needs to rebuild the light records (small next to the scene: 16 B per triangle)
+    std::vector<uint32_t> h_triangles, h_wide_index;
+    std::vector<RptMaterialData> h_materials;
+    std::vector<RptLightPickEntry> h_lights;
     DevBuf<LightBin> d_light_bins;
     DevBuf<LightRecord> d_light_records;
     uint32_t nbins = 0;
@@ -317,8 +323,8 @@ MegaParams mega_params(const rpt_context* c) {
 
 WideWorld wide_world(const rpt_context* c) {
     WideWorld w{};
-    w.bvh = WideScene{c->d_wide_nodes.p, c->d_tri_pos.p, kHalf1024Bytes};
-    w.tri_shade = c->d_tri_shade.p;
+    w.bvh = WideScene{c->tree.nodes, c->tree.tri_pos, kHalf1024Bytes};
+    w.tri_shade = c->tree.tri_shade;
     w.shade_stride = c->shade_stride;
     w.materials = c->d_materials.p;
     w.nmaterials = c->nmaterials;
@@ -564,13 +570,13 @@ extern "C" int rpt_destroy(rpt_context* c) {
         cudaStreamDestroy(c->copy_stream);
     }
     c->drain_stage_events();
-    for (auto* b : {&c->w_ray_o, &c->w_ray_d, &c->w_thr, &c->w_rad, &c->w_sh_o, &c->w_sh_d, &c->w_sh_c, &c->d_tri_pos,
-                    &c->d_tri_shade, &c->d_sky, &c->d_output})
+    c->tree.release();
+    for (auto* b : {&c->w_ray_o, &c->w_ray_d, &c->w_thr, &c->w_rad, &c->w_sh_o, &c->w_sh_d, &c->w_sh_c, &c->d_sky, &c->d_output})
         b->release();
     c->w_hit.release(); c->w_stack_overflow.release(); c->w_q0.release(); c->w_q1.release(); c->w_qhit.release(); c->w_qmiss.release(); c->w_qshaded.release();
     c->w_qshadow.release(); c->w_ctl.release();
     c->d_counters.release(); c->d_vertices.release(); c->d_triangles.release(); c->d_nodes.release(); c->d_materials.release();
-    c->d_lights.release(); c->d_atlas.release(); c->d_wide_nodes.release(); c->d_light_bins.release(); c->d_light_records.release();
+    c->d_lights.release(); c->d_atlas.release(); c->d_light_bins.release(); c->d_light_records.release();
     c->d_rng.release(); c->d_rgb.release(); c->d_rgba8.release(); c->d_ids.release(); c->d_pixel_map.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -609,12 +615,78 @@ void host_parallel_for(uint32_t n, Fn&& fn) {
 }
 }  // namespace
 
+namespace {
+
+// light-pick table -> bins over compact light records (a one-entry table with ratio < 0 is the sentinel: no bins).
+// `wide_index`: caller's triangle index -> leaf order.
+int build_light_records(rpt_context* c, const RptPerVertexData* vertices, const uint32_t* triangles, uint32_t ntriangles, const RptMaterialData* materials,
+                        const RptLightPickEntry* lights, uint32_t nlights, const uint32_t* wide_index, std::vector<LightBin>& bins, std::vector<LightRecord>& records) {
+    bins.clear();
+    records.clear();
+    if (nlights == 1 && lights[0].ratio < 0.0f) return RPT_OK;
+    std::unordered_map<uint32_t, uint32_t> record_of;
+    int status = RPT_OK;
+    auto record = [&](uint32_t tri_index, float area, float pdf) -> uint32_t {
+        auto it = record_of.find(tri_index);
+        if (it != record_of.end()) return it->second;
+        if (tri_index >= ntriangles) { status = RPT_ERR_INVALID_ARGUMENT; return 0; }
+        const uint32_t* tri = triangles + 4 * (size_t)tri_index;
+        const RptPerVertexData &a = vertices[tri[0]], &b = vertices[tri[1]], &cc = vertices[tri[2]];
+        LightRecord r{};
+        r.a_area = make_float4(a.vertex[0], a.vertex[1], a.vertex[2], area);
+        r.e1_pdf = make_float4(b.vertex[0] - a.vertex[0], b.vertex[1] - a.vertex[1], b.vertex[2] - a.vertex[2], pdf);
+        const uint32_t wi = wide_index[tri_index];
+        float wbits;
+        std::memcpy(&wbits, &wi, 4);
+        r.e2_tri = make_float4(cc.vertex[0] - a.vertex[0], cc.vertex[1] - a.vertex[1], cc.vertex[2] - a.vertex[2], wbits);
+        r.normal = make_float4(((a.normal[0] + b.normal[0]) + cc.normal[0]) / 3.0f, ((a.normal[1] + b.normal[1]) + cc.normal[1]) / 3.0f,
+                               ((a.normal[2] + b.normal[2]) + cc.normal[2]) / 3.0f, 0.0f);
+        const float* em = materials[tri[3]].emissive;
+        r.emission = make_float4(em[0], em[1], em[2], 0.0f);
+        const uint32_t id = (uint32_t)records.size();
+        records.push_back(r);
+        record_of.emplace(tri_index, id);
+        return id;
+    };
+    bins.reserve(nlights);
+    for (uint32_t i = 0; i < nlights; ++i) {
+        const RptLightPickEntry& e = lights[i];
+        LightBin bin{};
+        bin.light_a = record(e.triangle_index_a, e.triangle_area_a, e.triangle_pick_pdf_a);
+        // entries that were never topped up keep index_b = 0 with probability_b = 0: ratio == 1, never picked
+        bin.light_b = e.ratio >= 1.0f ? bin.light_a : record(e.triangle_index_b, e.triangle_area_b, e.triangle_pick_pdf_b);
+        bin.ratio = e.ratio;
+        bins.push_back(bin);
+    }
+    if (status != RPT_OK) return c->fail(status, "light-pick table references a triangle out of range");
+    if (records.size() >= (1u << 23)) return c->fail(RPT_ERR_UNSUPPORTED, "more than 2^23 emissive triangles (the path state keeps the sampled light in 23 bits)");
+    return RPT_OK;
+}
+
+int upload_light_records(rpt_context* c, const std::vector<LightBin>& bins, const std::vector<LightRecord>& records) {
+    c->d_light_bins.release();
+    c->d_light_records.release();
+    if (!bins.empty()) {
+        RPT_CUDA(c, c->d_light_bins.upload(bins.data(), bins.size(), c->stream));
+        RPT_CUDA(c, c->d_light_records.upload(records.data(), records.size(), c->stream));
+        RPT_CUDA(c, cudaStreamSynchronize(c->stream));  // (the vectors are the caller's locals)
+    }
+    c->nbins = (uint32_t)bins.size();
+    return RPT_OK;
+}
+
+}  // namespace
+
+// nodes == NULL (and nnodes == 0): no reference BVH is supplied — the wide tree is built on the device
+// (device_build.cu); triangle ids still refer to the caller's index buffer.
 extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices, uint32_t nvertices, const uint32_t* triangles,
                                 uint32_t ntriangles, const RptBVHNode* nodes, uint32_t nnodes, const RptMaterialData* materials,
                                 uint32_t nmaterials, const RptLightPickEntry* lights, uint32_t nlights, const uint8_t* atlas_rgba8,
                                 uint32_t atlas_w, uint32_t atlas_h, const float* sky_rgba32f, uint32_t sky_w, uint32_t sky_h) {
     if (!c) return RPT_ERR_INVALID_ARGUMENT;
-    if (!vertices || !triangles || !nodes || !materials || !lights || nvertices == 0 || ntriangles == 0 || nnodes == 0 || nmaterials == 0 || nlights == 0)
+    const bool build_on_device = nodes == nullptr && nnodes == 0;
+    if (!vertices || !triangles || (!nodes && !build_on_device) || !materials || !lights || nvertices == 0 || ntriangles == 0 || (nnodes == 0 && !build_on_device) ||
+        nmaterials == 0 || nlights == 0)
         return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: null or empty buffer");
     if (ntriangles >= 0x80000000u) return c->fail(RPT_ERR_UNSUPPORTED, "more than 2^31 triangles");
     if ((atlas_rgba8 && (atlas_w == 0 || atlas_h == 0)) || (sky_rgba32f && (sky_w == 0 || sky_h == 0)))
@@ -622,14 +694,6 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     for (size_t t = 0; t < (size_t)ntriangles; ++t)
         if (triangles[4 * t + 3] >= nmaterials) return c->fail(RPT_ERR_INVALID_ARGUMENT, "triangle %zu references material %u of %u", t, triangles[4 * t + 3], nmaterials);
     RPT_TRY(bind_device(c));
-
-    // ---- private re-layout (host side, once per scene).  Nothing of the context is touched until the input has
-    // been validated and every host-side layout built: a rejected scene leaves the previous world in place.
-    WideBvh wide;
-    const char* err = "";
-    if (!build_wide_bvh(nodes, nnodes, triangles, ntriangles, vertices, nvertices, wide, &err)) return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: %s", err);
-    if (wide.max_depth + 1 > kWideStackCapacity)
-        return c->fail(RPT_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%u)", wide.max_depth, kWideStackCapacity);
 
     bool any_normal_map = false;
     for (uint32_t m = 0; m < nmaterials; ++m) any_normal_map |= materials[m].has_normal_texture != 0;
@@ -639,75 +703,58 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
         return false;
     }();
     if (textured && !atlas_rgba8) return c->fail(RPT_ERR_INVALID_ARGUMENT, "a material is textured but no atlas was supplied");
-
-    // per-triangle shading records in wide order (layout: device_scene.h; three scattered vertex reads per triangle,
-    // shared out over the host threads).  a / e1 / e2 are copied from the traversal stream, so shading sees the bits
-    // the ray/triangle test saw.
     const uint32_t shade_stride = any_normal_map ? kShadeStrideTangents : kShadeStridePlain;
-    UninitVector<float> shade;
-    shade.resize((size_t)ntriangles * shade_stride * 4);
-    host_parallel_for(ntriangles, [&](uint32_t begin, uint32_t end) {
-        for (uint32_t wi = begin; wi < end; ++wi) {
-            const uint32_t* tri = triangles + 4 * (size_t)wide.orig_index[wi];
-            const RptPerVertexData &a = vertices[tri[0]], &b = vertices[tri[1]], &cc = vertices[tri[2]];
-            const float* pos = wide.tri_pos.data() + 12 * (size_t)wi;
-            float* o = shade.data() + (size_t)shade_stride * 4 * wi;
-            o[0] = pos[0]; o[1] = pos[1]; o[2] = pos[2]; o[3] = pos[7];  // a, bits(material)
-            o[4] = pos[4]; o[5] = pos[5]; o[6] = pos[6]; o[7] = a.uv0[0];
-            o[8] = pos[8]; o[9] = pos[9]; o[10] = pos[10]; o[11] = a.uv0[1];
-            o[12] = a.normal[0]; o[13] = a.normal[1]; o[14] = a.normal[2]; o[15] = b.uv0[0];
-            o[16] = b.normal[0]; o[17] = b.normal[1]; o[18] = b.normal[2]; o[19] = b.uv0[1];
-            o[20] = cc.normal[0]; o[21] = cc.normal[1]; o[22] = cc.normal[2]; o[23] = cc.uv0[0];
-            o[24] = cc.uv0[1];
-            if (any_normal_map) {
-                for (int k = 0; k < 3; ++k) { o[25 + k] = a.tangent[k]; o[28 + k] = b.tangent[k]; o[31 + k] = cc.tangent[k]; }
-                for (int k = 34; k < 40; ++k) o[k] = 0.0f;
-            } else {
-                for (int k = 25; k < 32; ++k) o[k] = 0.0f;
-            }
-        }
-    });
 
-    // light-pick table -> bins over compact light records (a one-entry table with ratio < 0 is the sentinel)
-    std::vector<LightBin> bins;
-    std::vector<LightRecord> records;
-    if (!(nlights == 1 && lights[0].ratio < 0.0f)) {
-        std::unordered_map<uint32_t, uint32_t> record_of;
-        auto record = [&](uint32_t tri_index, float area, float pdf, int& status) -> uint32_t {
-            auto it = record_of.find(tri_index);
-            if (it != record_of.end()) return it->second;
-            if (tri_index >= ntriangles) { status = RPT_ERR_INVALID_ARGUMENT; return 0; }
-            const uint32_t* tri = triangles + 4 * (size_t)tri_index;
-            const RptPerVertexData &a = vertices[tri[0]], &b = vertices[tri[1]], &cc = vertices[tri[2]];
-            LightRecord r{};
-            r.a_area = make_float4(a.vertex[0], a.vertex[1], a.vertex[2], area);
-            r.e1_pdf = make_float4(b.vertex[0] - a.vertex[0], b.vertex[1] - a.vertex[1], b.vertex[2] - a.vertex[2], pdf);
-            uint32_t wi = wide.wide_index[tri_index];
-            float wbits;
-            std::memcpy(&wbits, &wi, 4);
-            r.e2_tri = make_float4(cc.vertex[0] - a.vertex[0], cc.vertex[1] - a.vertex[1], cc.vertex[2] - a.vertex[2], wbits);
-            r.normal = make_float4(((a.normal[0] + b.normal[0]) + cc.normal[0]) / 3.0f, ((a.normal[1] + b.normal[1]) + cc.normal[1]) / 3.0f,
-                                   ((a.normal[2] + b.normal[2]) + cc.normal[2]) / 3.0f, 0.0f);
-            const float* em = materials[tri[3]].emissive;
-            r.emission = make_float4(em[0], em[1], em[2], 0.0f);
-            const uint32_t id = (uint32_t)records.size();
-            records.push_back(r);
-            record_of.emplace(tri_index, id);
-            return id;
-        };
-        int status = RPT_OK;
-        bins.reserve(nlights);
-        for (uint32_t i = 0; i < nlights; ++i) {
-            const RptLightPickEntry& e = lights[i];
-            LightBin bin{};
-            bin.light_a = record(e.triangle_index_a, e.triangle_area_a, e.triangle_pick_pdf_a, status);
-            // entries that were never topped up keep index_b = 0 with probability_b = 0: ratio == 1, never picked
-            bin.light_b = e.ratio >= 1.0f ? bin.light_a : record(e.triangle_index_b, e.triangle_area_b, e.triangle_pick_pdf_b, status);
-            bin.ratio = e.ratio;
-            bins.push_back(bin);
-        }
-        if (status != RPT_OK) return c->fail(status, "light-pick table references a triangle out of range");
-        if (records.size() >= (1u << 23)) return c->fail(RPT_ERR_UNSUPPORTED, "more than 2^23 emissive triangles (the path state keeps the sampled light in 23 bits)");
+    // ---- private re-layout.  Nothing of the context is touched until the input has been validated and every
+    // host-side layout built: a rejected scene leaves the previous world in place.
+    WideBvh wide;
+    UninitVector<float> shade;
+    float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};
+    if (!build_on_device) {
+        const char* err = "";
+        if (!build_wide_bvh(nodes, nnodes, triangles, ntriangles, vertices, nvertices, wide, &err)) return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: %s", err);
+        if (wide.max_depth + 1 > kWideStackCapacity)
+            return c->fail(RPT_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%u)", wide.max_depth, kWideStackCapacity);
+        // per-triangle shading records in wide order (layout: device_scene.h; three scattered vertex reads per triangle,
+        // shared out over the host threads).  a / e1 / e2 are copied from the traversal stream, so shading sees the bits
+        // the ray/triangle test saw.
+        shade.resize((size_t)ntriangles * shade_stride * 4);
+        host_parallel_for(ntriangles, [&](uint32_t begin, uint32_t end) {
+            for (uint32_t wi = begin; wi < end; ++wi) {
+                const uint32_t* tri = triangles + 4 * (size_t)wide.orig_index[wi];
+                const RptPerVertexData &a = vertices[tri[0]], &b = vertices[tri[1]], &cc = vertices[tri[2]];
+                const float* pos = wide.tri_pos.data() + 12 * (size_t)wi;
+                float* o = shade.data() + (size_t)shade_stride * 4 * wi;
+                o[0] = pos[0]; o[1] = pos[1]; o[2] = pos[2]; o[3] = pos[7];  // a, bits(material)
+                o[4] = pos[4]; o[5] = pos[5]; o[6] = pos[6]; o[7] = a.uv0[0];
+                o[8] = pos[8]; o[9] = pos[9]; o[10] = pos[10]; o[11] = a.uv0[1];
+                o[12] = a.normal[0]; o[13] = a.normal[1]; o[14] = a.normal[2]; o[15] = b.uv0[0];
+                o[16] = b.normal[0]; o[17] = b.normal[1]; o[18] = b.normal[2]; o[19] = b.uv0[1];
+                o[20] = cc.normal[0]; o[21] = cc.normal[1]; o[22] = cc.normal[2]; o[23] = cc.uv0[0];
+                o[24] = cc.uv0[1];
+                if (any_normal_map) {
+                    for (int k = 0; k < 3; ++k) { o[25 + k] = a.tangent[k]; o[28 + k] = b.tangent[k]; o[31 + k] = cc.tangent[k]; }
+                    for (int k = 34; k < 40; ++k) o[k] = 0.0f;
+                } else {
+                    for (int k = 25; k < 32; ++k) o[k] = 0.0f;
+                }
+            }
+        });
+        for (int k = 0; k < 3; ++k) { scene_lo[k] = nodes[0].aabb_min[k]; scene_hi[k] = nodes[0].aabb_max[k]; }  // (the binary root holds the scene bounds)
+    } else {
+        // what build_wide_bvh checks on its way: indices in range, no infinite / astronomically large coordinate
+        std::atomic<int> bad{0};
+        host_parallel_for(ntriangles, [&](uint32_t begin, uint32_t end) {
+            for (uint32_t t = begin; t < end; ++t)
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t v = triangles[4 * (size_t)t + k];
+                    if (v >= nvertices) { bad.store(1); return; }
+                    const float* p = vertices[v].vertex;
+                    if (std::fabs(p[0]) > 1e15f || std::fabs(p[1]) > 1e15f || std::fabs(p[2]) > 1e15f) { bad.store(2); return; }
+                }
+        });
+        if (bad.load() == 1) return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: triangle references a vertex out of range");
+        if (bad.load() == 2) return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_upload_world: vertex coordinate infinite or beyond 1e15");
     }
 
     // ---- uploads (from here on the previous world is gone, whatever happens)
@@ -716,20 +763,54 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     cudaStream_t s = c->stream;
     RPT_CUDA(c, c->d_vertices.upload(vertices, nvertices, s));
     RPT_CUDA(c, c->d_triangles.upload(reinterpret_cast<const uint4*>(triangles), ntriangles, s));
-    RPT_CUDA(c, c->d_nodes.upload(nodes, nnodes, s));
     RPT_CUDA(c, c->d_materials.upload(materials, nmaterials, s));
     RPT_CUDA(c, c->d_lights.upload(lights, nlights, s));
-    RPT_CUDA(c, c->d_wide_nodes.upload(reinterpret_cast<const uint4*>(wide.nodes.data()), wide.nodes.size() * 5, s));
-    RPT_CUDA(c, c->d_tri_pos.upload(reinterpret_cast<const float4*>(wide.tri_pos.data()), (size_t)ntriangles * 3, s));
-    RPT_CUDA(c, c->d_tri_shade.upload(reinterpret_cast<const float4*>(shade.data()), (size_t)ntriangles * shade_stride, s));
-    c->shade_stride = shade_stride;
-    c->d_light_bins.release();
-    c->d_light_records.release();
-    if (!bins.empty()) {
-        RPT_CUDA(c, c->d_light_bins.upload(bins.data(), bins.size(), s));
-        RPT_CUDA(c, c->d_light_records.upload(records.data(), records.size(), s));
+    c->tree.release();
+    uint32_t max_depth = 0;
+    std::vector<uint32_t> wide_index;
+    if (!build_on_device) {
+        RPT_CUDA(c, c->d_nodes.upload(nodes, nnodes, s));
+        RPT_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tree.nodes), wide.nodes.size() * sizeof(WideNode)));
+        RPT_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tree.tri_pos), (size_t)ntriangles * 48));
+        RPT_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tree.tri_shade), (size_t)ntriangles * shade_stride * 16));
+        RPT_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tree.orig_index), (size_t)ntriangles * 4));
+        RPT_CUDA(c, cudaMemcpyAsync(c->tree.nodes, wide.nodes.data(), wide.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, s));
+        RPT_CUDA(c, cudaMemcpyAsync(c->tree.tri_pos, wide.tri_pos.data(), (size_t)ntriangles * 48, cudaMemcpyHostToDevice, s));
+        RPT_CUDA(c, cudaMemcpyAsync(c->tree.tri_shade, shade.data(), (size_t)ntriangles * shade_stride * 16, cudaMemcpyHostToDevice, s));
+        RPT_CUDA(c, cudaMemcpyAsync(c->tree.orig_index, wide.orig_index.data(), (size_t)ntriangles * 4, cudaMemcpyHostToDevice, s));
+        c->tree.nnodes = (uint32_t)wide.nodes.size();
+        c->tree.max_depth = max_depth = wide.max_depth;
+        wide_index = std::move(wide.wide_index);
+    } else {
+        c->d_nodes.release();
+        const cudaError_t e = device_build_wide_bvh(c->d_vertices.p, c->d_triangles.p, ntriangles, shade_stride, c->tree, s);
+        if (e != cudaSuccess) return c->fail(RPT_ERR_CUDA, "device BVH build: %s", cudaGetErrorString(e));
+        max_depth = c->tree.max_depth;
+        if (max_depth + 1 > kWideStackCapacity) {
+            c->tree.release();
+            return c->fail(RPT_ERR_UNSUPPORTED, "device-built BVH depth %u exceeds the traversal stack (%u)", max_depth, kWideStackCapacity);
+        }
+        wide_index.resize(ntriangles);
+        RPT_CUDA(c, cudaMemcpyAsync(wide_index.data(), c->tree.wide_index, (size_t)ntriangles * 4, cudaMemcpyDeviceToHost, s));
+        float box[6];
+        RPT_CUDA(c, cudaMemcpyAsync(box, c->tree.node_box, sizeof box, cudaMemcpyDeviceToHost, s));  // node 0: the scene bounds
+        RPT_CUDA(c, cudaStreamSynchronize(s));
+        for (int k = 0; k < 3; ++k) { scene_lo[k] = box[k]; scene_hi[k] = box[3 + k]; }
     }
-    c->nbins = (uint32_t)bins.size();
+    c->device_built = build_on_device;
+    c->shade_stride = shade_stride;
+    c->ntriangles = ntriangles;
+    c->nvertices = nvertices;
+
+    std::vector<LightBin> bins;
+    std::vector<LightRecord> records;
+    RPT_TRY(build_light_records(c, vertices, triangles, ntriangles, materials, lights, nlights, wide_index.data(), bins, records));
+    RPT_TRY(upload_light_records(c, bins, records));
+    c->h_triangles.assign(triangles, triangles + 4 * (size_t)ntriangles);
+    c->h_materials.assign(materials, materials + nmaterials);
+    c->h_lights.assign(lights, lights + nlights);
+    c->h_wide_index = std::move(wide_index);
+
     const uchar4 white = make_uchar4(255, 255, 255, 255);
     if (atlas_rgba8) {
         RPT_CUDA(c, c->d_atlas.upload(reinterpret_cast<const uchar4*>(atlas_rgba8), (size_t)atlas_w * atlas_h, s));
@@ -740,10 +821,8 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     }
     const float magenta[16] = {1, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1};  // fallback_gpu_image, src/asset.rs:275-281
     c->sources_finite = true;
-    for (int k = 0; k < 3; ++k) {  // (the binary root holds the scene bounds)
-        const float lo = nodes[0].aabb_min[k], hi = nodes[0].aabb_max[k];
-        if (!(std::fabs(lo) < 1e15f) || !(std::fabs(hi) < 1e15f)) c->sources_finite = false;
-    }
+    for (int k = 0; k < 3; ++k)
+        if (!(std::fabs(scene_lo[k]) < 1e15f) || !(std::fabs(scene_hi[k]) < 1e15f)) c->sources_finite = false;
     if (sky_rgba32f) {
         std::atomic<bool> finite{true};
         host_parallel_for((uint32_t)std::min<uint64_t>((uint64_t)sky_w * sky_h, 0xFFFFFFFFull), [&](uint32_t begin, uint32_t end) {
@@ -761,11 +840,56 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     RPT_CUDA(c, cudaStreamSynchronize(s));  // host staging vectors die at return
     c->nlights = nlights;
     c->nmaterials = nmaterials;
-    c->deep_tree = wide.max_depth + 1 > kWideStackShared;
+    c->deep_tree = max_depth + 1 > kWideStackShared;
     if (c->deep_tree && c->wave_capacity != 0 && !c->w_stack_overflow.p)
         RPT_CUDA(c, c->w_stack_overflow.alloc(trace_stack_overflow_entries(c->sm_count * c->trace_blocks_per_sm)));
     c->has_world = true;
     return RPT_OK;
+}
+
+// Vertices moved, topology unchanged (same triangles, same materials): new vertex records are uploaded, the triangle
+// streams are rewritten and every box of the tree is refitted bottom-up on the device (device_build.cu).  `lights` may
+// carry a new light-pick table (areas and pick pdfs change when emitters deform); NULL keeps the table and only
+// refreshes the emitters' geometry.
+extern "C" int rpt_refit_world(rpt_context* c, const RptPerVertexData* vertices, uint32_t nvertices, const RptLightPickEntry* lights, uint32_t nlights) {
+    if (!c || !vertices) return RPT_ERR_INVALID_ARGUMENT;
+    if (!c->has_world) return c->fail(RPT_ERR_NOT_READY, "rpt_refit_world before rpt_upload_world");
+    if (nvertices != c->nvertices) return c->fail(RPT_ERR_SIZE_MISMATCH, "world has %u vertices, refit got %u", c->nvertices, nvertices);
+    if (lights && nlights == 0) return c->fail(RPT_ERR_INVALID_ARGUMENT, "empty light table");
+    RPT_TRY(bind_device(c));
+    std::atomic<int> bad{0};
+    host_parallel_for(nvertices, [&](uint32_t begin, uint32_t end) {
+        for (uint32_t v = begin; v < end; ++v) {
+            const float* p = vertices[v].vertex;
+            if (std::fabs(p[0]) > 1e15f || std::fabs(p[1]) > 1e15f || std::fabs(p[2]) > 1e15f) { bad.store(1); return; }
+        }
+    });
+    if (bad.load()) return c->fail(RPT_ERR_INVALID_ARGUMENT, "rpt_refit_world: vertex coordinate infinite or beyond 1e15");
+    std::vector<LightBin> bins;
+    std::vector<LightRecord> records;
+    const RptLightPickEntry* table = lights ? lights : c->h_lights.data();
+    const uint32_t ntable = lights ? nlights : (uint32_t)c->h_lights.size();
+    RPT_TRY(build_light_records(c, vertices, c->h_triangles.data(), c->ntriangles, c->h_materials.data(), table, ntable, c->h_wide_index.data(), bins, records));
+    const bool had_lights = c->nbins > 0;
+    if (had_lights != !bins.empty() || bins.size() != c->d_light_bins.n || records.size() != c->d_light_records.n) c->drop_graphs();  // light buffers move
+    RPT_CUDA(c, cudaMemcpyAsync(c->d_vertices.p, vertices, (size_t)nvertices * sizeof(RptPerVertexData), cudaMemcpyHostToDevice, c->stream));
+    const cudaError_t e = device_refit_wide_bvh(c->d_vertices.p, c->d_triangles.p, c->ntriangles, c->shade_stride, c->tree, c->stream);
+    if (e != cudaSuccess) return c->fail(RPT_ERR_CUDA, "device BVH refit: %s", cudaGetErrorString(e));
+    if (bins.size() == c->d_light_bins.n && records.size() == c->d_light_records.n && !bins.empty()) {  // same shape: in place, captured graphs stay valid
+        RPT_CUDA(c, cudaMemcpyAsync(c->d_light_bins.p, bins.data(), bins.size() * sizeof(LightBin), cudaMemcpyHostToDevice, c->stream));
+        RPT_CUDA(c, cudaMemcpyAsync(c->d_light_records.p, records.data(), records.size() * sizeof(LightRecord), cudaMemcpyHostToDevice, c->stream));
+    } else {
+        RPT_TRY(upload_light_records(c, bins, records));
+    }
+    if (lights) {
+        RPT_CUDA(c, c->d_lights.upload(lights, nlights, c->stream));
+        c->h_lights.assign(lights, lights + nlights);
+        c->nlights = nlights;
+    }
+    // the reference-layout node copy (megakernel arm) is NOT refitted: that arm needs a fresh rpt_upload_world
+    c->d_nodes.release();
+    c->device_built = true;
+    return c->cuda(cudaStreamSynchronize(c->stream), "rpt_refit_world");
 }
 
 // ============================================================================ render state
@@ -908,6 +1032,7 @@ extern "C" int rpt_enqueue(rpt_context* c, uint32_t n_samples) {
     }
     int status = RPT_OK;
     if (c->pipeline == RPT_PIPELINE_MEGAKERNEL) {
+        if (!c->d_nodes.p) return c->fail(RPT_ERR_NOT_READY, "the megakernel arm traverses the reference BVH, and this world has none (device-built or refitted tree)");
         c->launch(RPT_STAGE_MEGAKERNEL, [&] { launch_mega_trace(mega_params(c), n_samples, c->stream); });
         status = c->cuda(cudaGetLastError(), "megakernel launch");
         // the megakernel counts its rays on the device; finished paths are counted here
@@ -1058,6 +1183,7 @@ extern "C" int rpt_read_primary_ids(rpt_context* c, uint32_t* ids, size_t npixel
     RPT_CUDA(c, cudaStreamSynchronize(c->stream));
     int status = RPT_OK;
     if (c->pipeline == RPT_PIPELINE_MEGAKERNEL) {
+        if (!c->d_nodes.p) return c->fail(RPT_ERR_NOT_READY, "the megakernel arm traverses the reference BVH, and this world has none (device-built or refitted tree)");
         launch_mega_primary(mega_params(c), c->d_ids.p, c->stream);
         c->kernel_launches++;
         status = c->cuda(cudaGetLastError(), "primary-id launch");

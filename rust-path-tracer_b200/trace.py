@@ -65,8 +65,15 @@ class Renderer:
             pass
 
     # ---- scene / state -------------------------------------------------------------------
-    def upload_world(self, world: World, skybox: np.ndarray | None = None):
-        """skybox: (H, W, 4) float32 lat-long texels or None (2x2 magenta fallback)."""
+    def refit_world(self, per_vertex_buffer: np.ndarray, light_pick_buffer: np.ndarray | None = None):
+        """Vertices moved, topology unchanged: refit the tree on the device (rpt_refit_world)."""
+        v = np.ascontiguousarray(per_vertex_buffer)
+        l = None if light_pick_buffer is None else np.ascontiguousarray(light_pick_buffer)
+        self._call("rpt_refit_world", capi.ptr(v), C.c_uint32(len(v)), capi.ptr(l), C.c_uint32(0 if l is None else len(l)))
+
+    def upload_world(self, world: World, skybox: np.ndarray | None = None, build_on_device: bool = False):
+        """skybox: (H, W, 4) float32 lat-long texels or None (2x2 magenta fallback).  build_on_device: do not hand over
+        the reference BVH; the backend builds its tree on the GPU (world.nodes may then be None)."""
         atlas = None if world.atlas is None else np.ascontiguousarray(world.atlas, np.uint8)
         sky = None if skybox is None else np.ascontiguousarray(skybox, np.float32)
         u32 = C.c_uint32
@@ -74,7 +81,7 @@ class Renderer:
             "rpt_upload_world",
             capi.ptr(world.per_vertex_buffer), u32(len(world.per_vertex_buffer)),
             capi.ptr(world.index_buffer), u32(len(world.index_buffer)),
-            capi.ptr(world.nodes), u32(len(world.nodes)),
+            None if build_on_device else capi.ptr(world.nodes), u32(0 if build_on_device else len(world.nodes)),
             capi.ptr(world.material_data_buffer), u32(len(world.material_data_buffer)),
             capi.ptr(world.light_pick_buffer), u32(len(world.light_pick_buffer)),
             capi.ptr(atlas), u32(0 if atlas is None else atlas.shape[1]), u32(0 if atlas is None else atlas.shape[0]),
