@@ -15,7 +15,14 @@
 
 namespace rpt {
 
-constexpr int kShadeBlock = 256;
+#ifndef RPT_SHADE_BLOCK
+#define RPT_SHADE_BLOCK 256
+#endif
+#ifndef RPT_SHADE_MIN_BLOCKS
+#define RPT_SHADE_MIN_BLOCKS 4
+#endif
+constexpr int kShadeBlock = RPT_SHADE_BLOCK;
+constexpr int kShadeMinBlocks = RPT_SHADE_MIN_BLOCKS;  // resident blocks per SM the register allocation aims at
 constexpr uint32_t kSmemMaterials = 64;  // 6 KB
 
 // A light-table word: plain (shared-memory) load when the table is staged, read-only global load otherwise.
@@ -32,7 +39,7 @@ __device__ __forceinline__ uint32_t wave_pixel(const WaveDesc& d, uint32_t j) {
 // wf_compact_shaded_kernel turns those words into the next extend queue and the shadow queue, in order.
 // The shadow ray itself is stored at index i (sh_o / sh_d / sh_c), the next ray in the path's own slot.
 template <bool MATS_IN_SMEM, bool LIGHTS_IN_SMEM, bool TANGENTS>
-__global__ void __launch_bounds__(kShadeBlock, 4) wf_shade_kernel(FrameParams f, WideWorld w, WaveState s, WaveDesc d, const uint2* __restrict__ rng,
+__global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) wf_shade_kernel(FrameParams f, WideWorld w, WaveState s, WaveDesc d, const uint2* __restrict__ rng,
                                                                uint32_t bounce) {
     __shared__ RptMaterialData sm_materials[MATS_IN_SMEM ? kSmemMaterials : 1];
     __shared__ __align__(16) uint32_t sm_lights[LIGHTS_IN_SMEM ? kSmemLightBytes / 4 : 4];  // records first (16-byte aligned), then bins
@@ -256,7 +263,7 @@ void launch_wf_shade(const WaveLaunch& l, const FrameParams& f, const WideWorld&
     const bool mats = w.nmaterials <= kSmemMaterials;
     const bool lights = w.nbins > 0u && (size_t)w.nlights * sizeof(LightRecord) + (size_t)w.nbins * sizeof(LightBin) <= kSmemLightBytes;
     const bool tangents = w.shade_stride == kShadeStrideTangents;
-    const dim3 grid(l.grid * 4);
+    const dim3 grid(l.grid * kShadeMinBlocks);
 #define RPT_SHADE(M, L, T) wf_shade_kernel<M, L, T><<<grid, kShadeBlock, 0, l.stream>>>(f, w, s, d, rng, bounce)
     if (mats && lights && tangents) RPT_SHADE(true, true, true);
     else if (mats && lights) RPT_SHADE(true, true, false);

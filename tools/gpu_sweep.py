@@ -14,7 +14,7 @@ for setting in sys.argv[3:] or [""]:
         k, v = kv.split("=")
         os.environ[k] = v
     with Renderer(0) as r:
-        r.upload_world(world, sky); r.set_config(cfg); r.write_rng(seeds)
+        r.upload_world(world, sky, build_on_device=os.environ.get('SWEEP_DEVICE_BUILD') == '1'); r.set_config(cfg); r.write_rng(seeds)
         for _ in range(3):  # direct run, graph capture, first replay
             r.enqueue(spp)
         r.sync()

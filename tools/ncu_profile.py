@@ -7,10 +7,11 @@ extend kernel (nearest-hit trace), the shadow-connect kernel (any-hit trace) and
 render (tools/prof_run.py, CUDA graphs off so every launch is visible), reads the reports back with `ncu -i ... --page
 raw --csv`, and writes
 
-    profiles/kernel_profiles.json        per workload and kernel: duration, warp instructions (per ray / per hit),
+    gpurun_out/profiles/kernel_profiles.json  (copy to profiles/)
+                                                per workload and kernel: duration, warp instructions (per ray / per hit),
                                          lanes per instruction, issue-slot utilisation, pipe utilisation, L1 / L2 hit
                                          rates, DRAM bytes (per ray / per hit) — with the git hash of the capture
-    profiles/<tag>_<kernel>_<workload>_ncu_summary.txt   the tracked metrics + the heaviest SASS basic blocks
+    gpurun_out/profiles/<tag>_<kernel>_<workload>_ncu_summary.txt   the tracked metrics + the heaviest SASS basic blocks
 
 The .ncu-rep files land in gpurun_out/ (scratch).  Numbers printed by a run under ncu are never bench values.
 """
@@ -26,7 +27,7 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(REPO, "gpurun_out")
-PROFILES = os.path.join(REPO, "profiles")
+PROFILES = os.path.join(OUT, "profiles")  # only gpurun_out/ travels back from the box: copy these into profiles/ afterwards
 
 KERNELS = {
     # name: (ncu -k regex, kernel-name filter, unit of work)
@@ -132,9 +133,10 @@ def main():
     ap.add_argument("--spp", type=int, default=4)
     ap.add_argument("--tag", default="r2")
     args = ap.parse_args()
-    os.makedirs(OUT, exist_ok=True)
+    os.makedirs(PROFILES, exist_ok=True)
     path = os.path.join(PROFILES, "kernel_profiles.json")
-    table = json.load(open(path)) if os.path.exists(path) else {}
+    committed = os.path.join(REPO, "profiles", "kernel_profiles.json")  # workloads not captured this time keep their entries
+    table = json.load(open(committed)) if os.path.exists(committed) else {}
     table["git"] = args.git_hash
     table["captured"] = datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%dT%H:%MZ")
     table["how"] = "python tools/ncu_profile.py (ncu --set full --clock-control none, every launch of one wave of tools/prof_run.py, graphs off; sums over the bounces)"
