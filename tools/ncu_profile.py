@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--kernels", nargs="+", default=list(KERNELS))
     ap.add_argument("--spp", type=int, default=4)
     ap.add_argument("--tag", default="r2")
+    ap.add_argument("--keep-reports", action="store_true", help="keep the .ncu-rep files (tens of MB each; gpurun brings back 64 MiB at most)")
     args = ap.parse_args()
     os.makedirs(PROFILES, exist_ok=True)
     path = os.path.join(PROFILES, "kernel_profiles.json")
@@ -151,6 +152,9 @@ def main():
             rep, work = reports[regex]
             table[workload][kernel] = summarize(rep, kernel, workload, work, args.tag, args.git_hash)
             print(workload, kernel, json.dumps({k: v for k, v in table[workload][kernel].items() if k != "per_bounce"})[:400], flush=True)
+        if not args.keep_reports:
+            for rep, _ in reports.values():
+                os.remove(rep)
     with open(path, "w") as f:
         json.dump(table, f, indent=1, sort_keys=True)
 
