@@ -101,6 +101,8 @@ def summarize(rep, kernel, workload, work, tag, git_hash):
         "kernel_name": mine[0][0] if mine else "", "launches": f"all {len(per_bounce)} bounces of one {workload} wave ({spp_of(workload)} spp)", unit_name: tot["units"],
         "duration_ms": tot["ms"], f"warp_instructions_per_{one}": tot["inst"] / tot["units"], "lanes_per_instruction": tot["thread_inst"] / tot["inst"],
         "issue_active_pct_of_peak": tot["issue_weighted"] / tot["ms"], f"dram_bytes_per_{one}": tot["dram"] / tot["units"],
+        "l1_hit_pct": sum(b["l1_hit_pct"] * b["duration_ms"] for b in per_bounce) / tot["ms"],
+        "l2_hit_pct": sum(b["l2_hit_pct"] * b["duration_ms"] for b in per_bounce) / tot["ms"],
         "per_bounce": per_bounce, "source": os.path.basename(rep) + " (ncu --set full --clock-control none)",
     }
     csv_path = rep.replace(".ncu-rep", ".csv")
