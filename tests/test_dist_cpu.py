@@ -76,3 +76,29 @@ def test_tile_partition_is_a_partition(w, h, n):
     for r, p in enumerate(parts):
         x, y = p % w, p // w
         assert (((y // 32) * ((w + 31) // 32) + x // 32) % n == r).all()
+
+
+def test_tracing_state_keeps_the_stop_word_in_step_with_its_flags():
+    """`rpt_enqueue_interruptible` polls ONE word; TracingState derives it from running / interacting / dirty the way the
+    reference's dispatch loop combines its atomics (src/trace.rs:187-193): stop = interacting | dirty | !running."""
+    from rust_path_tracer_b200.trace import TracingState, setup_trace
+
+    s = TracingState(8, 8)
+    assert s.stop_flag[0] == 1  # not running yet
+    s.running = True
+    assert s.stop_flag[0] == 0
+    s.interacting = True
+    assert s.stop_flag[0] == 1 and s.interacting
+    s.interacting = False
+    s.dirty = True
+    assert s.stop_flag[0] == 1
+    s.dirty = False
+    assert s.stop_flag[0] == 0
+    s.running = False
+    assert s.stop_flag[0] == 1
+    t = setup_trace(8, 8, 4)
+    assert t.running and t.stop_flag[0] == 0
+    t.samples = 4
+    t._watch()  # the watcher clears `running` once enough samples are in
+    assert not t.running and t.stop_flag[0] == 1
+    assert not setup_trace(8, 8, 0).running  # 0 samples requested: stopped at once ("startup" benches)
