@@ -112,6 +112,8 @@ struct rpt_context {
     int trace_blocks_per_sm = 9;  // = the __launch_bounds__ of wf_trace_kernel: 56 registers, 36 warps per SM
     int refill_below = 20;
     // deferred triangle tests (wf_trace_deferred_kernel): RPT_DEFER_EXTEND / RPT_DEFER_SHADOW / RPT_FLUSH_AT / RPT_FLUSH_KEEP
+    bool l2_persist = false;     // RPT_L2_PERSIST=1: access-policy window over the scene (measured: extend -0.8 %, shade +16 % — the set-aside is L2 the shading stage loses)
+    size_t l2_window_bytes = 0;
     bool defer_extend = false, defer_shadow = false;  // measured: -2 % extend time on the 1M-triangle proxy, +3.5 % on DarkCornell — off
     int flush_at = 12, flush_keep = 6;
     // Paths whose throughput is exactly zero are retired instead of traced to their first roulette (RPT_KEEP_DEAD_PATHS=1
@@ -539,6 +541,7 @@ extern "C" int rpt_create(int device_id, rpt_context** out_ctx) {
     if (const char* v = getenv("RPT_TRACE_BLOCKS_PER_SM")) c->trace_blocks_per_sm = std::max(1, atoi(v));
     if (const char* v = getenv("RPT_REFILL_BELOW")) c->refill_below = atoi(v);
     if (const char* v = getenv("RPT_LOG_QUEUES")) c->log_queues = atoi(v) != 0;
+    if (const char* v = getenv("RPT_L2_PERSIST")) c->l2_persist = atoi(v) != 0;
     if (const char* v = getenv("RPT_DEFER_EXTEND")) c->defer_extend = atoi(v) != 0;
     if (const char* v = getenv("RPT_DEFER_SHADOW")) c->defer_shadow = atoi(v) != 0;
     if (const char* v = getenv("RPT_FLUSH_AT")) c->flush_at = atoi(v);
@@ -663,6 +666,28 @@ int build_light_records(rpt_context* c, const RptPerVertexData* vertices, const 
     return RPT_OK;
 }
 
+// The trace kernels' scene data (wide nodes + triangle positions: 63 MB for a million triangles) fits the 126 MB L2, but
+// the shading stage streams gigabytes of path state, shading records and texels through it between two extend
+// launches.  An access-policy window marks the scene range as PERSISTING in the L2 set-aside, so node and triangle
+// fetches that miss the L1 keep hitting the L2.  Best effort: a device without the feature just runs without it.
+void pin_scene_in_l2(rpt_context* c, const void* base, size_t bytes) {
+    c->l2_window_bytes = 0;
+    if (!c->l2_persist || !base || bytes == 0) return;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) { cudaGetLastError(); return; }
+    const size_t window = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    const size_t carve = std::min(window, (size_t)prop.persistingL2CacheMaxSize);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    attr.accessPolicyWindow.num_bytes = window;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) { cudaGetLastError(); return; }
+    c->l2_window_bytes = window;
+}
+
 int upload_light_records(rpt_context* c, const std::vector<LightBin>& bins, const std::vector<LightRecord>& records) {
     c->d_light_bins.release();
     c->d_light_records.release();
@@ -770,8 +795,12 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
     std::vector<uint32_t> wide_index;
     if (!build_on_device) {
         RPT_CUDA(c, c->d_nodes.upload(nodes, nnodes, s));
-        RPT_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tree.nodes), wide.nodes.size() * sizeof(WideNode)));
-        RPT_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tree.tri_pos), (size_t)ntriangles * 48));
+        // nodes and triangle positions — everything the trace kernels read of the scene — in ONE allocation, so that a
+        // single L2 access-policy window can cover them (pin_scene_in_l2)
+        const size_t node_bytes = (wide.nodes.size() * sizeof(WideNode) + 255) & ~(size_t)255;
+        RPT_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tree.nodes), node_bytes + (size_t)ntriangles * 48));
+        c->tree.tri_pos = reinterpret_cast<float4*>(reinterpret_cast<char*>(c->tree.nodes) + node_bytes);
+        c->tree.tri_pos_in_nodes_block = true;
         RPT_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tree.tri_shade), (size_t)ntriangles * shade_stride * 16));
         RPT_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->tree.orig_index), (size_t)ntriangles * 4));
         RPT_CUDA(c, cudaMemcpyAsync(c->tree.nodes, wide.nodes.data(), wide.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, s));
@@ -798,6 +827,8 @@ extern "C" int rpt_upload_world(rpt_context* c, const RptPerVertexData* vertices
         for (int k = 0; k < 3; ++k) { scene_lo[k] = box[k]; scene_hi[k] = box[3 + k]; }
     }
     c->device_built = build_on_device;
+    pin_scene_in_l2(c, c->tree.nodes, build_on_device ? (size_t)c->tree.nnodes * sizeof(WideNode)
+                                                      : (size_t)(reinterpret_cast<char*>(c->tree.tri_pos) - reinterpret_cast<char*>(c->tree.nodes)) + (size_t)ntriangles * 48);
     c->shade_stride = shade_stride;
     c->ntriangles = ntriangles;
     c->nvertices = nvertices;

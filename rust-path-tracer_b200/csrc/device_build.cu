@@ -437,7 +437,7 @@ done:
 }
 
 void DeviceBuildResult::release() {
-    for (void* p : {(void*)nodes, (void*)tri_pos, (void*)tri_shade, (void*)orig_index, (void*)wide_index, (void*)level_nodes, node_box})
+    for (void* p : {(void*)nodes, tri_pos_in_nodes_block ? nullptr : (void*)tri_pos, (void*)tri_shade, (void*)orig_index, (void*)wide_index, (void*)level_nodes, node_box})
         if (p) cudaFree(p);
     *this = DeviceBuildResult{};
 }

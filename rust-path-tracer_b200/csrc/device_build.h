@@ -22,6 +22,7 @@ struct DeviceBuildResult {
     void* node_box = nullptr;        // one float[6] box per node (scratch of the bottom-up fit)
     std::vector<uint32_t> level_offsets;  // level L = level_nodes[level_offsets[L] .. level_offsets[L + 1])
     uint32_t nnodes = 0, max_depth = 0;
+    bool tri_pos_in_nodes_block = false;  // tri_pos points into the allocation of `nodes` (one range for the L2 window)
     void release();
 };
 
