@@ -164,3 +164,36 @@ def test_start_up_with_a_device_build_of_the_proxy():
     assert float((d_ids != ids).mean()) <= ID_BUDGET
     assert helpers.mae(d_out[:, :3] / 4, out[:, :3] / 4)[0] <= MAE_TOLERANCE
     assert times[True] < 0.5, times
+
+
+@pytest.mark.parametrize("kind", ["some_nan", "all_nan", "huge_range"])
+def test_non_finite_and_extreme_vertices(kind):
+    """NaN coordinates are ignored by every min / max and such triangles are never hit (as in the reference); a scene
+    spanning many orders of magnitude still quantises conservatively; infinite coordinates are refused."""
+    scene = _soup(600, seed=5)
+    v = scene.vertices.copy()
+    if kind == "some_nan":
+        v[::97, 0] = np.nan
+    elif kind == "all_nan":
+        v[:, :3] = np.nan
+    else:
+        v[:300, :3] *= np.float32(1e-3)   # a cloud of tiny triangles around the origin ...
+        v[300:330, :3] *= np.float32(3e3)  # ... and a few enormous ones
+    scene = BakedScene(v, scene.normals, scene.tangents, scene.uvs, scene.indices, scene.materials)
+    world = World.from_baked(scene)
+    cfg, seeds = helpers.config(96, 64, 0), helpers.seeds(96, 64)
+    _, _, _, o_ids = om.trace(cfg, om.OracleScene(world), seeds, 1, want_primary_ids=True)
+    out, ids, _ = render(world, cfg, seeds, 2, build_on_device=True)
+    host_out, host_ids, _ = render(world, cfg, seeds, 2, build_on_device=False)
+    np.testing.assert_array_equal(ids, host_ids)  # both of the product's trees agree exactly ...
+    assert float((ids != o_ids).mean()) <= 2e-3   # ... and with the reference up to ties between overlapping random triangles
+    if kind == "all_nan":
+        assert (ids == 0xFFFFFFFF).all()
+    inf = v.copy()
+    inf[5, 1] = np.inf
+    bad = World(world.per_vertex_buffer.copy(), world.index_buffer, None, world.material_data_buffer, world.light_pick_buffer)
+    bad.per_vertex_buffer["vertex"][5, 1] = np.inf
+    with Renderer(0) as r:
+        with pytest.raises(capi.RptError) as e:
+            r.upload_world(bad, build_on_device=True)
+        assert e.value.code == capi.ERR_INVALID_ARGUMENT
