@@ -6,11 +6,12 @@
 // start-up — `rpt_upload_world(nodes = NULL)` and `rpt_refit_world`:
 //
 //   build   Morton codes of the triangle centroids (63 bits) -> radix sort (cub) -> the wide tree is cut straight out of
-//           the sorted codes, level by level: a node owns a run of codes, finds the highest bit TRIPLE in which its run
-//           differs and splits there into up to eight children — the triple IS the octant slot the traversal's
-//           `slot ^ octant` order expects (x the most significant bit).  Runs of <= 3 triangles become leaf slots,
-//           longer ones child nodes (contiguous, in slot order); a node's leaf triangles get one contiguous range of the
-//           triangle stream, in slot order, as wide_bvh.h lays down.  Runs of identical codes split evenly.
+//           the sorted codes, level by level: a node owns a run of codes and cuts it into up to eight sub-runs by
+//           repeated binary splits (largest sub-run first, at the highest bit in which it differs), so nodes come out
+//           full; the axes those splits decide give each sub-run its octant slot, which is what the traversal's
+//           `slot ^ octant` order expects (x the most significant bit of a Morton triple).  Sub-runs of one triangle (up to
+//           three with RPT_DEVICE_BUILD_MAX_LEAF) become leaf slots, longer ones child nodes (contiguous, in slot order); a node's leaf triangles get one
+//           contiguous range of the triangle stream, in slot order, as wide_bvh.h lays down.  Identical codes split in halves.
 //   fit     bottom-up over the levels: slot boxes from the triangles' vertices / the child nodes' boxes, node box,
 //           power-of-two cell, conservative 8-bit quantisation — the arithmetic of Collapser::encode.
 //   emit    triangle position stream and shading records in the new leaf order.
@@ -23,6 +24,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -108,58 +110,84 @@ struct BuildCounters {
     uint32_t pad;
 };
 
-// first index in [lo, hi) whose triple (code >> shift) & 7 is >= c
-__device__ __forceinline__ uint32_t lower_bound_triple(const unsigned long long* codes, uint32_t lo, uint32_t hi, int shift, uint32_t c) {
+// first index in [lo, hi) whose code has bit `bit` set (the run is sorted and agrees on every higher bit)
+__device__ __forceinline__ uint32_t first_with_bit(const unsigned long long* codes, uint32_t lo, uint32_t hi, int bit) {
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (((uint32_t)(codes[mid] >> shift) & 7u) < c) lo = mid + 1; else hi = mid;
+        if ((codes[mid] >> bit) & 1ull) hi = mid; else lo = mid + 1;
     }
     return lo;
 }
 
+
+// One node per thread.  The node's run of sorted codes is cut into up to eight sub-runs by repeated BINARY splits — always
+// the largest remaining sub-run, at the highest bit in which it differs — so nodes come out full (a fixed split at one
+// bit triple leaves most octree cells empty).  Every split decides one axis of the two halves' octant (bit % 3: x is the
+// most significant bit of a Morton triple); a sub-run takes the slot of its octant, its undecided axes used to resolve
+// collisions, so `slot ^ ray octant` still visits near children first.  Sub-runs of <= kMaxLeafTriangles become leaf slots.
 __global__ void split_level_kernel(const unsigned long long* __restrict__ codes, const uint32_t* __restrict__ sorted_ids, const Task* __restrict__ tasks,
                                    uint32_t ntasks, Task* __restrict__ next, BuildCounters* __restrict__ ctr, uint32_t* __restrict__ node_words,
-                                   uint32_t* __restrict__ orig_index) {
+                                   uint32_t* __restrict__ orig_index, uint32_t kMaxLeafTriangles) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntasks) return;
     const Task t = tasks[i];
-    const uint32_t n = t.hi - t.lo;
-    uint32_t bound[9];
-    uint32_t nslots;
-    if (n <= 3u) {  // (only the root of a tiny scene gets here: one leaf slot)
-        bound[0] = t.lo; bound[1] = t.hi;
-        nslots = 1u;
-    } else {
-        const unsigned long long x = codes[t.lo] ^ codes[t.hi - 1u];
-        if (x == 0ull) {  // identical codes (coincident centroids): even parts
-            nslots = min(8u, (n + 2u) / 3u);
-            for (uint32_t c = 0; c <= nslots; ++c) bound[c] = t.lo + (uint32_t)(((unsigned long long)n * c) / nslots);
+    uint32_t lo[8], hi[8], known[8], side[8];
+    uint32_t nruns = 1;
+    lo[0] = t.lo; hi[0] = t.hi; known[0] = 0u; side[0] = 0u;
+    while (nruns < 8u) {
+        uint32_t best = 8u, best_count = 1u;
+        for (uint32_t r = 0; r < nruns; ++r)
+            if (hi[r] - lo[r] > best_count) { best = r; best_count = hi[r] - lo[r]; }
+        if (best == 8u) break;  // nothing left with more than one triangle
+        const unsigned long long x = codes[lo[best]] ^ codes[hi[best] - 1u];
+        uint32_t mid, axis = 3u;
+        if (x == 0ull) {
+            mid = lo[best] + best_count / 2u;  // identical codes (coincident centroids): halves
         } else {
-            const int shift = ((63 - __clzll((long long)x)) / 3) * 3;  // the highest triple in which the run differs
-            nslots = 8u;
-            bound[0] = t.lo;
-            for (uint32_t c = 1; c < 8u; ++c) bound[c] = lower_bound_triple(codes, t.lo, t.hi, shift, c);
-            bound[8] = t.hi;
+            const int bit = 63 - __clzll((long long)x);
+            mid = first_with_bit(codes, lo[best], hi[best], bit);
+            axis = (uint32_t)bit % 3u;
         }
+        lo[nruns] = mid; hi[nruns] = hi[best]; known[nruns] = known[best]; side[nruns] = side[best];
+        hi[best] = mid;
+        if (axis < 3u && !((known[best] >> axis) & 1u)) {  // the first split along an axis places the halves on its two sides
+            known[best] |= 1u << axis; known[nruns] |= 1u << axis;
+            side[nruns] |= 1u << axis;
+        }
+        ++nruns;
+    }
+    // octant slots: the decided axes are binding, the undecided ones are free to dodge a collision
+    int run_in_slot[8];
+    for (int k = 0; k < 8; ++k) run_in_slot[k] = -1;
+    for (uint32_t r = 0; r < nruns; ++r) {
+        int slot = -1;
+        for (uint32_t f = 0; f < 8u && slot < 0; ++f) {  // f: bits tried on the undecided axes
+            if (f & known[r]) continue;
+            const uint32_t cand = (side[r] & known[r]) | f;
+            if (run_in_slot[cand] < 0) slot = (int)cand;
+        }
+        for (uint32_t cand = 0; cand < 8u && slot < 0; ++cand)
+            if (run_in_slot[cand] < 0) slot = (int)cand;
+        run_in_slot[slot] = (int)r;
     }
     uint32_t imask = 0, valid = 0, n_inner = 0, n_leaf_tris = 0;
-    for (uint32_t s = 0; s < nslots; ++s) {
-        const uint32_t cnt = bound[s + 1] - bound[s];
-        if (cnt == 0u) continue;
-        if (cnt <= 3u) { valid |= ((1u << cnt) - 1u) << (3u * s); n_leaf_tris += cnt; }
+    for (uint32_t s = 0; s < 8u; ++s) {
+        if (run_in_slot[s] < 0) continue;
+        const uint32_t cnt = hi[run_in_slot[s]] - lo[run_in_slot[s]];
+        if (cnt <= kMaxLeafTriangles) { valid |= ((1u << cnt) - 1u) << (3u * s); n_leaf_tris += cnt; }
         else { imask |= 1u << s; ++n_inner; }
     }
     const uint32_t child_base = n_inner ? atomicAdd(&ctr->nodes, n_inner) : 0u;
     const uint32_t task_base = n_inner ? atomicAdd(&ctr->next_tasks, n_inner) : 0u;
     const uint32_t tri_base = n_leaf_tris ? atomicAdd(&ctr->triangles, n_leaf_tris) : 0u;
     uint32_t ci = 0, ti = 0;
-    for (uint32_t s = 0; s < nslots; ++s) {
-        const uint32_t cnt = bound[s + 1] - bound[s];
-        if (cnt == 0u) continue;
-        if (cnt <= 3u) {
-            for (uint32_t k = 0; k < cnt; ++k) orig_index[tri_base + ti++] = sorted_ids[bound[s] + k];
+    for (uint32_t s = 0; s < 8u; ++s) {
+        if (run_in_slot[s] < 0) continue;
+        const uint32_t first = lo[run_in_slot[s]], cnt = hi[run_in_slot[s]] - first;
+        if (cnt <= kMaxLeafTriangles) {
+            for (uint32_t k = 0; k < cnt; ++k) orig_index[tri_base + ti++] = sorted_ids[first + k];
         } else {
-            next[task_base + ci] = Task{bound[s], bound[s + 1], child_base + ci};
+            next[task_base + ci] = Task{first, first + cnt, child_base + ci};
             ++ci;
         }
     }
@@ -346,6 +374,9 @@ cudaError_t device_build_wide_bvh(const RptPerVertexData* d_verts, const uint4* 
     const uint32_t max_nodes = std::max(ntris, 1u);  // every inner node has at least two children: fewer nodes than leaves
     std::vector<uint32_t> level_offsets;
     uint32_t levels = 0;
+    // triangles per leaf slot (1..3, wide_bvh.h): fewer = tighter leaf boxes and fewer ray/triangle tests, more nodes
+    uint32_t max_leaf = 1;  // measured (proxy / DarkCornell, Mpaths/s): 3 -> 596 / 939, 2 -> 624 / 940, 1 -> 642 / 962
+    if (const char* v = std::getenv("RPT_DEVICE_BUILD_MAX_LEAF")) max_leaf = (uint32_t)std::min(3, std::max(1, std::atoi(v)));
 
     RPT_CK(dev_alloc(&d_bounds, 6));
     RPT_CK(dev_alloc(&d_codes, ntris)); RPT_CK(dev_alloc(&d_codes_sorted, ntris));
@@ -386,7 +417,7 @@ cudaError_t device_build_wide_bvh(const RptPerVertexData* d_verts, const uint4* 
         Task *cur = d_tasks_a, *nxt = d_tasks_b;
         while (ntasks) {
             ++levels;
-            split_level_kernel<<<blocks_for(ntasks), kThreads, 0, stream>>>(d_codes_sorted, d_ids_sorted, cur, ntasks, nxt, d_ctr, reinterpret_cast<uint32_t*>(out.nodes), out.orig_index);
+            split_level_kernel<<<blocks_for(ntasks), kThreads, 0, stream>>>(d_codes_sorted, d_ids_sorted, cur, ntasks, nxt, d_ctr, reinterpret_cast<uint32_t*>(out.nodes), out.orig_index, max_leaf);
             BuildCounters c{};
             RPT_CK(cudaMemcpyAsync(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost, stream));
             RPT_CK(cudaStreamSynchronize(stream));

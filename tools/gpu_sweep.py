@@ -19,9 +19,12 @@ for setting in sys.argv[3:] or [""]:
             r.enqueue(spp)
         r.sync()
         r.reset_counters(); r.enqueue(spp); ms = r.device_ms(); c = r.counters()
-        r.set_stage_timing(True); r.enqueue(spp); st = r.stage_timing()
+        r.set_stage_timing(True); r.enqueue(spp); st = r.stage_timing(); r.set_stage_timing(False)
+        r.set_trace_statistics(True); r.reset_counters(); r.enqueue(spp); ts = r.trace_statistics(); r.set_trace_statistics(False)
     rays = c["nearest_rays"] + c["any_rays"]
     print(f"{workload} [{setting}] {c['paths']/ms/1e3:8.1f} Mpaths/s {rays/ms/1e3:8.1f} Mrays/s | " +
-          " ".join(f"{k}={v[0]:.1f}" for k, v in st.items() if v[1]), flush=True)
+          " ".join(f"{k}={v[0]:.1f}" for k, v in st.items() if v[1]) +
+          f" | per nearest ray: {ts['nearest_node_visits'] / max(ts['nearest_rays'], 1):.2f} visits, {ts['nearest_triangle_tests'] / max(ts['nearest_rays'], 1):.2f} tests"
+          f"; per any ray: {ts['any_node_visits'] / max(ts['any_rays'], 1):.2f}, {ts['any_triangle_tests'] / max(ts['any_rays'], 1):.2f}", flush=True)
     for kv in filter(None, setting.split(",")):
         os.environ.pop(kv.split("=")[0], None)
