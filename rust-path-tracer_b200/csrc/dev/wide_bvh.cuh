@@ -48,7 +48,24 @@ struct WideScene {
     // literal here would be folded into that slot and the selectors rematerialised in registers instead
     uint32_t half_1024_bytes;
 };
+// Plane de-quantisation, two builds (RPT_PLANES_FP32):
+//   0  fp16 pairs: one PRMT builds (1024 + q_j, 1024 + q_k) as two halves (0x64 = high byte of 1024.0h), two conversions
+//      widen them — 2 instructions per plane byte, the conversions on the FMA-side pipe;
+//   1  fp32 directly: one PRMT per plane byte builds the float 32768 + q (0x47000000 = 32768.0f, the byte lands in
+//      mantissa bits 8..15, whose unit is exactly 1 at that exponent) — 1.5 instructions per plane byte, all of the
+//      de-quantisation on the 16-lane ALU pipe.  The larger bias rounds the folded addend more coarsely (below).
+#ifndef RPT_PLANES_FP32
+#define RPT_PLANES_FP32 0
+#endif
+#if RPT_PLANES_FP32
+constexpr uint32_t kHalf1024Bytes = 0x00004700u;  // bytes 0x00 and 0x47 for the PRMT that builds 32768 + q
+constexpr float kPlaneBias = 32768.0f;
+constexpr float kPadCells = 16640.0f;  // 256 (box extent) + 16384: the addend is rounded at magnitude 32768 |adj|, i.e. by < 2^-9 |adj| = 3255 x 6e-7 cells
+#else
 constexpr uint32_t kHalf1024Bytes = 0x64646464u;  // 0x64 = high byte of 1024.0 in fp16
+constexpr float kPlaneBias = 1024.0f;
+constexpr float kPadCells = 768.0f;
+#endif
 
 struct WideHit {
     float t;            // 1e6 if no hit (kernels/src/intersection.rs:68)
@@ -113,16 +130,28 @@ RPT_D unsigned long long dequant_pair(uint32_t word, uint32_t magic, uint32_t se
     asm("{.reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h;}" : "=f"(lo), "=f"(hi) : "r"(h2));
     return pack_f32x2(lo, hi);
 }
+#if RPT_PLANES_FP32
+// (32768 + byte LO, 32768 + byte LO + 1) as two floats: result bytes (0x00, word byte, 0x00, 0x47), selector 0x5404 | byte << 4
+RPT_D void slab_pair(uint32_t word, uint32_t magic, uint32_t lo_byte, float adj, float org, float& t0, float& t1) {
+    const float q0 = __uint_as_float(__byte_perm(word, magic, 0x5404u | (lo_byte << 4)));
+    const float q1 = __uint_as_float(__byte_perm(word, magic, 0x5404u | ((lo_byte + 1u) << 4)));
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack_f32x2(q0, q1)), "l"(pack_f32x2(adj, adj)), "l"(pack_f32x2(org, org)));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(r));
+}
+#define RPT_PAIR_SEL(LO) (LO)
+#else
 RPT_D void slab_pair(uint32_t word, uint32_t magic, uint32_t sel, float adj, float org, float& t0, float& t1) {
     unsigned long long r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(dequant_pair(word, magic, sel)), "l"(pack_f32x2(adj, adj)), "l"(pack_f32x2(org, org)));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(r));
 }
 #define RPT_PAIR_SEL(LO) (0x4140u + 0x0202u * ((LO) / 2u))
+#endif
 #else
 inline void slab_pair(uint32_t word, uint32_t, uint32_t lo_byte, float adj, float org, float& t0, float& t1) {
-    t0 = fmaf(1024.0f + (float)((word >> (8u * lo_byte)) & 0xFFu), adj, org);
-    t1 = fmaf(1024.0f + (float)((word >> (8u * lo_byte + 8u)) & 0xFFu), adj, org);
+    t0 = fmaf(kPlaneBias + (float)((word >> (8u * lo_byte)) & 0xFFu), adj, org);
+    t1 = fmaf(kPlaneBias + (float)((word >> (8u * lo_byte + 8u)) & 0xFFu), adj, org);
 }
 #define RPT_PAIR_SEL(LO) (LO)
 #endif
@@ -221,13 +250,13 @@ struct WideCursor {
         // product with idir and the final FMA are each correctly rounded and idir is within 1 ulp of 1/d, i.e.
         // together off by < 3 * 2^-23 of |p - o| resp. of the box extent (<= 256 cells): pad by 5 * 2^-23 (6e-7) of both.  Folding the -1024 bias of the fp16
         // de-quantisation into the addend rounds it at magnitude 1024 |adj|, i.e. by < 2^-14 |adj|: 512 more
-        // cells in the same pad term cover that four times over.
+        // cells in the same pad term cover that four times over.  (RPT_PLANES_FP32: bias 32768, rounded by < 2^-9 |adj|: kPadCells.)
         const f3 rel_o = p - ray.o;
-        const f3 apad = mk3(fabsf(fmaf(768.0f, cell.x, fabsf(rel_o.x)) * ray.idir.x) * 6e-7f, fabsf(fmaf(768.0f, cell.y, fabsf(rel_o.y)) * ray.idir.y) * 6e-7f,
-                            fabsf(fmaf(768.0f, cell.z, fabsf(rel_o.z)) * ray.idir.z) * 6e-7f);
+        const f3 apad = mk3(fabsf(fmaf(kPadCells, cell.x, fabsf(rel_o.x)) * ray.idir.x) * 6e-7f, fabsf(fmaf(kPadCells, cell.y, fabsf(rel_o.y)) * ray.idir.y) * 6e-7f,
+                            fabsf(fmaf(kPadCells, cell.z, fabsf(rel_o.z)) * ray.idir.z) * 6e-7f);
         const f3 org = rel_o * ray.idir;
-        const f3 org_near = mk3(fmaf(adj.x, -1024.0f, org.x - apad.x), fmaf(adj.y, -1024.0f, org.y - apad.y), fmaf(adj.z, -1024.0f, org.z - apad.z));
-        const f3 org_far = mk3(fmaf(adj.x, -1024.0f, org.x + apad.x), fmaf(adj.y, -1024.0f, org.y + apad.y), fmaf(adj.z, -1024.0f, org.z + apad.z));
+        const f3 org_near = mk3(fmaf(adj.x, -kPlaneBias, org.x - apad.x), fmaf(adj.y, -kPlaneBias, org.y - apad.y), fmaf(adj.z, -kPlaneBias, org.z - apad.z));
+        const f3 org_far = mk3(fmaf(adj.x, -kPlaneBias, org.x + apad.x), fmaf(adj.y, -kPlaneBias, org.y + apad.y), fmaf(adj.z, -kPlaneBias, org.z + apad.z));
 
         const bool nx = (ray.oct_inv & 4u) == 0u, ny = (ray.oct_inv & 2u) == 0u, nz = (ray.oct_inv & 1u) == 0u;  // d.x < 0, ...
         // children 0..3 and 4..7: near/far byte words per axis depend on the ray's sign
