@@ -83,10 +83,20 @@ RPT_HD uint32_t octant_permute(uint32_t oct, uint32_t m) {
 }
 
 // Ray constants hoisted out of the node loop.
+// RPT_NODE_INDEXED_LOADS (device builds): the near / far plane words of a node are LOADED from the place the ray's
+// signs point at (three per-ray byte offsets) instead of loading all six pairs and choosing with twelve SELs — the
+// selection moves off the half-rate ALU pipe onto the load unit.
+#ifndef RPT_NODE_INDEXED_LOADS
+#define RPT_NODE_INDEXED_LOADS 0
+#endif
+
 struct WideRay {
     f3 o, d;
     f3 idir;        // 1 / d with |d| clamped away from 0
     uint32_t oct_inv;  // dx>=0 ? 4 : 0 | dy>=0 ? 2 : 0 | dz>=0 ? 1 : 0
+#if RPT_NODE_INDEXED_LOADS && defined(__CUDACC__)
+    uint32_t near_x, near_y, near_z;  // which of a node's ten 8-byte words holds the planes the ray enters first, per axis
+#endif
 };
 
 // 1 / d with |d| clamped away from 0.  It only feeds the conservative box tests, so the device uses the 1-ulp
@@ -109,6 +119,12 @@ RPT_D WideRay make_wide_ray(f3 o, f3 d) {
     r.d = d;
     r.idir = mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
     r.oct_inv = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
+#if RPT_NODE_INDEXED_LOADS && defined(__CUDACC__)
+    // a node as ten 8-byte words: qlo_x 4, qlo_y 5, qlo_z 6, qhi_x 7, qhi_y 8, qhi_z 9 (wide_bvh.h)
+    r.near_x = d.x < 0.0f ? 7u : 4u;
+    r.near_y = d.y < 0.0f ? 8u : 5u;
+    r.near_z = d.z < 0.0f ? 9u : 6u;
+#endif
     return r;
 }
 
@@ -241,7 +257,16 @@ struct WideCursor {
     template <class Stack>
     RPT_D void visit_node(const WideScene& s, Stack& stack) {
         const uint4* node = s.nodes + 5u * (size_t)next;
+#if RPT_NODE_INDEXED_LOADS && defined(__CUDACC__)
+        const uint4 n0 = __ldg(node), n1 = __ldg(node + 1);
+        const uint2* words = reinterpret_cast<const uint2*>(s.nodes);  // (32-bit word indices: the address arithmetic stays IMAD / IMAD.WIDE)
+        const uint32_t w10 = 10u * next;
+        const uint2 near_wx = __ldg(words + (w10 + ray.near_x)), far_wx = __ldg(words + (w10 + 11u - ray.near_x));
+        const uint2 near_wy = __ldg(words + (w10 + ray.near_y)), far_wy = __ldg(words + (w10 + 13u - ray.near_y));
+        const uint2 near_wz = __ldg(words + (w10 + ray.near_z)), far_wz = __ldg(words + (w10 + 15u - ray.near_z));
+#else
         const uint4 n0 = __ldg(node), n1 = __ldg(node + 1), n2 = __ldg(node + 2), n3 = __ldg(node + 3), n4 = __ldg(node + 4);
+#endif
 
         const f3 p = mk3(as_float(n0.x), as_float(n0.y), as_float(n0.z));
         const f3 cell = mk3(as_float(n0.w), as_float(n1.w << 16), as_float(n1.w & 0xFFFF0000u));  // powers of two
@@ -258,12 +283,17 @@ struct WideCursor {
         const f3 org_near = mk3(fmaf(adj.x, -kPlaneBias, org.x - apad.x), fmaf(adj.y, -kPlaneBias, org.y - apad.y), fmaf(adj.z, -kPlaneBias, org.z - apad.z));
         const f3 org_far = mk3(fmaf(adj.x, -kPlaneBias, org.x + apad.x), fmaf(adj.y, -kPlaneBias, org.y + apad.y), fmaf(adj.z, -kPlaneBias, org.z + apad.z));
 
+#if RPT_NODE_INDEXED_LOADS && defined(__CUDACC__)
+        uint32_t h = test_four<0u>(s.half_1024_bytes, near_wx.x, near_wy.x, near_wz.x, far_wx.x, far_wy.x, far_wz.x, adj, org_near, org_far, best_t);
+        h |= test_four<4u>(s.half_1024_bytes, near_wx.y, near_wy.y, near_wz.y, far_wx.y, far_wy.y, far_wz.y, adj, org_near, org_far, best_t);
+#else
         const bool nx = (ray.oct_inv & 4u) == 0u, ny = (ray.oct_inv & 2u) == 0u, nz = (ray.oct_inv & 1u) == 0u;  // d.x < 0, ...
         // children 0..3 and 4..7: near/far byte words per axis depend on the ray's sign
         uint32_t h = test_four<0u>(s.half_1024_bytes, nx ? n3.z : n2.x, ny ? n4.x : n2.z, nz ? n4.z : n3.x, nx ? n2.x : n3.z, ny ? n2.z : n4.x, nz ? n3.x : n4.z, adj,
                                    org_near, org_far, best_t);
         h |= test_four<4u>(s.half_1024_bytes, nx ? n3.w : n2.y, ny ? n4.y : n2.w, nz ? n4.w : n3.y, nx ? n2.y : n3.w, ny ? n2.w : n4.y, nz ? n3.y : n4.w, adj,
                            org_near, org_far, best_t);
+#endif
         const uint32_t imask = n1.z >> 24;
         tgroup.x = n1.y;
         tvalid = n1.z & 0x00FFFFFFu;
