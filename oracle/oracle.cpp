@@ -14,6 +14,10 @@
 // Rust's f32::sin/cos/... call on Linux), and third-party arithmetic is restated from the
 // published behaviour of glam 0.22 (Vec3 scalar: dot = (x*x'+y*y')+z*z', normalize = v*(1/len),
 // lerp = a+(b-a)*s, Mat3*v = (c0*v.x+c1*v.y)+c2*v.z) and compiler-rt's powi.
+// Beyond that one pixel, tests/test_known_answers.py holds this file to answers that do not come from it: closed
+// forms and numpy quadrature of the reference's own formulas (diffuse-only and mirror-limit spheres, the lat-long sky
+// lookup), and laws its estimators obey by construction (an emitter seen from inside == a constant sky, constant
+// textures == constant factors, NEE off / MIS / direct-only agree, Russian roulette is unbiased) — tests/known_answers.py.
 //
 // Layout of this file (reference file it follows):
 //   vector helpers           glam 0.22 semantics
