@@ -218,3 +218,63 @@ def sky_lookup_prediction(width, height, sky, sun_direction, cam_rotation=(0.0, 
     top = s64[y0, x0] + (s64[y0, x1] - s64[y0, x0]) * fx[..., None]
     bot = s64[y1, x0] + (s64[y1, x1] - s64[y1, x0]) * fx[..., None]
     return (top + (bot - top) * fy[..., None]) * (sun_direction[3] / 15.0)
+
+
+def procedural_sky_prediction(width, height, sun_direction, cam_position=(0.0, 1.0, -5.0), cam_rotation=(0.0, 0.0)):
+    """numpy (float64) restatement of kernels/src/skybox.rs:18-94 for pixel-centre primary rays that miss everything:
+    12-step single scattering (Rayleigh + Mie) from the camera position, two-sample optical depth towards the sun,
+    phase functions, sqrt then ^2.2."""
+    ys, xs = np.mgrid[0:height, 0:width]
+    u = ((xs + 0.5) / width) * 2 - 1
+    v = ((1 - (ys + 0.5) / height) * 2 - 1) * (height / width)
+    d = np.stack([u, v, np.ones_like(u)], -1)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    rx, ry = cam_rotation
+    cx, sx, cy, sy = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry)
+    d = d @ (np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])).T
+    o = np.broadcast_to(np.asarray(cam_position, np.float64), d.shape)
+    sun = np.asarray(sun_direction[:3], np.float64)
+    ray_c = np.array([58e-7, 135e-7, 331e-7])
+    mie_s = np.full(3, 2e-5)
+    mie_e = mie_s * 1.1
+    earth, atmo, h_ray, h_mie = 6360e3, 6380e3, 8e3, 12e2
+    centre = np.array([0.0, -earth, 0.0])
+
+    def escape(p, dirs, r):
+        vv = p - centre
+        b = (vv * dirs).sum(-1)
+        det = b * b - (vv * vv).sum(-1) + r * r
+        root = np.sqrt(np.maximum(det, 0))
+        t = np.where(-b - root >= 0, -b - root, -b + root)
+        return np.where(det < 0, -1.0, t)
+
+    def densities(p):
+        h = np.maximum(np.linalg.norm(p - centre, axis=-1) - earth, 0.0)
+        return np.exp(-h / h_ray), np.exp(-h / h_mie)
+
+    steps = 12
+    depth = escape(o, d, atmo) / steps
+    i_r = np.zeros(d.shape)
+    i_m = np.zeros(d.shape)
+    tot_r = np.zeros(d.shape[:2])
+    tot_m = np.zeros(d.shape[:2])
+    sun_dirs = np.broadcast_to(sun, d.shape)
+    for i in range(steps):
+        p = o + d * (depth * i)[..., None]
+        dr, dm = densities(p)
+        dr, dm = dr * depth, dm * depth
+        tot_r += dr
+        tot_m += dm
+        l = escape(p, sun_dirs, atmo)
+        r0, m0 = densities(p)
+        r1, m1 = densities(p + sun_dirs * l[..., None])
+        sum_r = tot_r + r0 * (l / 2) + r1 * (l / 2)
+        sum_m = tot_m + m0 * (l / 2) + m1 * (l / 2)
+        a = np.exp(-ray_c[None, None, :] * sum_r[..., None] - mie_e[None, None, :] * sum_m[..., None])
+        i_r += a * dr[..., None]
+        i_m += a * dm[..., None]
+    mu = (d * sun).sum(-1)[..., None]
+    res = sun_direction[3] * (1 + mu * mu) * (i_r * ray_c * 0.0597 + i_m * mie_s * 0.0196 / (1.58 - 1.52 * mu) ** 1.5)
+    out = np.sqrt(res)
+    out = np.where(np.isfinite(out).all(-1, keepdims=True), out, 0.0)
+    return out ** 2.2
