@@ -95,6 +95,24 @@ def constant_texture_furnace_world(byte=118):
     return w_tex, w_ref
 
 
+@functools.lru_cache(maxsize=None)
+def flat_normal_map_sphere_world():
+    """The grey sphere with a FLAT normal map (texel (128, 128, 255): tangent-space normal (0.004, 0.004, 1)) through the
+    atlas: lib.rs:131-141 must hand the BSDF (almost exactly) the geometric normal, normalised."""
+    from rust_path_tracer_b200.atlas import pack_scene_textures
+    from rust_path_tracer_b200.world import World
+
+    base = _furnace_baked()
+    flat = np.empty((16, 16, 4), np.uint8)
+    flat[...] = (128, 128, 255, 255)
+    tex = [dict() for _ in base.materials]
+    tex[0] = {"normals": flat}
+    scene = _clone(base, indices=base.indices[base.indices[:, 3] == 0].copy(), textures=tex)
+    scene.uvs = (0.25 + 0.5 * (base.uvs - np.floor(base.uvs))).astype(np.float32)
+    atlas = pack_scene_textures(scene, 256, 256)
+    return World.from_baked(scene, atlas=atlas)
+
+
 def constant_sky(value=SHELL_EMISSION, width=8, height=4):
     img = np.empty((height, width, 4), np.float32)
     img[..., :3] = value

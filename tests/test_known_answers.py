@@ -8,6 +8,7 @@ What each case pins:
   sky_lookup            S2 / H3: lat-long mapping, yaw by the sun azimuth, bilinear polyfill (floor / ceil / wrap)
                         against a float64 numpy restatement of lib.rs:70-78 + image_polyfill.rs:32-55
   procedural_sky        S1: the 12-step Rayleigh + Mie scattering of skybox.rs against a float64 numpy restatement
+  flat_normal_map       H2: normal-map fetch, TBN, normalize — a flat map reproduces the diffuse-only closed form
   constant_textures     H3 / B1: albedo, roughness and metallic read through the atlas == the same constants as factors
   diffuse_only          B2 diffuse branch, create_cartesian, cosine sampling, Fresnel, H1 interpolation:
                         L * albedo * E[1 - Schlick(h.v)] by quadrature
@@ -143,6 +144,19 @@ def test_diffuse_only_sphere_in_a_constant_environment(render):
     assert npix > 400 and err.max() < 3e-3, err  # measured 2.4e-4
     inside = np.isfinite(want).all(-1)
     assert np.sqrt((((img[inside] - want[inside]) / want[inside]) ** 2).mean()) < 1e-2  # per pixel, 64 spp: measured 1.9e-3
+
+
+@pytest.mark.parametrize("render", BACKENDS)
+def test_flat_normal_map_changes_nothing_but_the_normalisation(render):
+    """H2 (lib.rs:131-141): atlas fetch of the normal texel, * 2 - 1, TBN, normalize.  A flat map must reproduce the
+    diffuse-only closed form (the interpolated normal is 0.1 % short of unit length without the map, unit with it)."""
+    world = ka.flat_normal_map_sphere_world()
+    assert world.material_data_buffer[0]["has_normal_texture"] == 1
+    cfg = helpers.config(S, S, 0, has_skybox=1, specular_weight_clamp=[0.0, 0.0])
+    img = render(world, cfg, helpers.seeds(S, S), 64, ka.constant_sky())
+    want = ka.diffuse_only_prediction(S, S, (0.18, 0.18, 0.18), ka.SHELL_EMISSION)
+    err, npix = ka.relative_error_of_mean(img, want)
+    assert np.isfinite(img).all() and npix > 400 and err.max() < 5e-3, err
 
 
 @pytest.mark.parametrize("render", BACKENDS)
