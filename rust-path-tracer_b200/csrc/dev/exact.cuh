@@ -60,10 +60,31 @@ RPT_D void camera_ray(const Camera& cam, uint32_t px, uint32_t py, Rng& rng, f3&
 // Takes the precomputed edges e1 = b - a, e2 = c - a (single IEEE subtractions, so computing
 // them once on the host changes no bit).  Returns true with t (>= 0) and the back-face flag;
 // the caller applies `t > 0.001 && t < best` (intersection.rs:195).
+// RPT_TRI_STRAIGHT (build switch): the same operations without the early returns — every value that decides or is
+// returned is computed by the identical instruction sequence, the four rejections are combined at the end (a rejected
+// triangle's later values, possibly inf / NaN, are discarded).  Straight-line code keeps all three record loads in flight
+// together (with the early returns ptxas sinks the load of `a` below the determinant test) at the price of finishing
+// tests that could have stopped early — which a warp only profits from when ALL of its active lanes stop.
+#ifndef RPT_TRI_STRAIGHT
+#define RPT_TRI_STRAIGHT 1
+#endif
 RPT_HD bool ray_triangle(f3 ro, f3 rd, f3 a, f3 e1, f3 e2, float& t_out, bool& backface) {
     const f3 pv = cross(rd, e2);
     const float det = dot(e1, pv);
     backface = signbit(det);
+#if RPT_TRI_STRAIGHT
+    {
+        const float inv_det = 1.0f / det;
+        const f3 tv = ro - a;
+        const float u = dot(tv, pv) * inv_det;
+        const f3 qv = cross(tv, e1);
+        const float v = dot(rd, qv) * inv_det;
+        const float t = dot(e2, qv) * inv_det;
+        t_out = t;
+        const bool reject = (fabsf(det) < 1e-6f) | (u < 0.0f) | (u > 1.0f) | (v < 0.0f) | (u + v > 1.0f) | (t < 0.0f);
+        return !reject;
+    }
+#endif
     if (fabsf(det) < 1e-6f) return false;
     const float inv_det = 1.0f / det;
     const f3 tv = ro - a;

@@ -47,17 +47,35 @@ struct TexelF32 {
     RPT_D f3 operator()(uint32_t i) const { return xyz(__ldg(texels + i)); }
 };
 
-template <class Fetch>
-RPT_D f3 sample_bilinear(const Fetch& fetch, uint32_t width, uint32_t height, uint32_t wmask, uint32_t hmask, float u, float v) {
+// The lookup in two halves: where the four taps are and how they are weighted, then the blend.
+struct BilinearTaps {
+    uint32_t i00, i10, i01, i11;
+    float fx, fy;
+};
+RPT_D BilinearTaps bilinear_taps(uint32_t width, uint32_t height, uint32_t wmask, uint32_t hmask, float u, float v) {
     const float sx = u * (float)width, sy = v * (float)height;
     const float flx = floorf(sx), fly = floorf(sy);
-    const float fx = sx - flx, fy = sy - fly;
-    const uint32_t x0 = wrap_coord(f32_as_i32_sat(flx), width, wmask), x1 = wrap_coord(f32_as_i32_sat(ceilf(sx)), width, wmask);
-    const uint32_t y0 = wrap_coord(f32_as_i32_sat(fly), height, hmask), y1 = wrap_coord(f32_as_i32_sat(ceilf(sy)), height, hmask);
-    const f3 c00 = fetch(y0 * width + x0), c10 = fetch(y0 * width + x1);
-    const f3 c01 = fetch(y1 * width + x0), c11 = fetch(y1 * width + x1);
+    const int cx0 = f32_as_i32_sat(flx), cx1 = f32_as_i32_sat(ceilf(sx)), cy0 = f32_as_i32_sat(fly), cy1 = f32_as_i32_sat(ceilf(sy));
+    uint32_t x0, x1, y0, y1;
+    if ((cx0 | cx1 | cy0 | cy1) >= 0 && wmask != 0u && hmask != 0u) {  // one test for the four coordinates: the usual case
+        x0 = (uint32_t)cx0 & wmask; x1 = (uint32_t)cx1 & wmask;
+        y0 = (uint32_t)cy0 & hmask; y1 = (uint32_t)cy1 & hmask;
+    } else {
+        x0 = wrap_coord(cx0, width, wmask); x1 = wrap_coord(cx1, width, wmask);
+        y0 = wrap_coord(cy0, height, hmask); y1 = wrap_coord(cy1, height, hmask);
+    }
+    return BilinearTaps{y0 * width + x0, y0 * width + x1, y1 * width + x0, y1 * width + x1, sx - flx, sy - fly};
+}
+RPT_D f3 bilinear_blend(f3 c00, f3 c10, f3 c01, f3 c11, float fx, float fy) {
     const f3 a = lerp3(c00, c10, fx), b = lerp3(c01, c11, fx);
     return lerp3(a, b, fy);
+}
+template <class Fetch>
+RPT_D f3 sample_bilinear(const Fetch& fetch, uint32_t width, uint32_t height, uint32_t wmask, uint32_t hmask, float u, float v) {
+    const BilinearTaps t = bilinear_taps(width, height, wmask, hmask, u, v);
+    const f3 c00 = fetch(t.i00), c10 = fetch(t.i10);
+    const f3 c01 = fetch(t.i01), c11 = fetch(t.i11);
+    return bilinear_blend(c00, c10, c01, c11, t.fx, t.fy);
 }
 
 struct Atlas {

@@ -89,6 +89,9 @@ RPT_HD uint32_t octant_permute(uint32_t oct, uint32_t m) {
 #ifndef RPT_NODE_INDEXED_LOADS
 #define RPT_NODE_INDEXED_LOADS 0
 #endif
+#ifndef RPT_NODE_SHORT_PAD
+#define RPT_NODE_SHORT_PAD 1
+#endif
 
 struct WideRay {
     f3 o, d;
@@ -256,6 +259,15 @@ struct WideCursor {
     // Tests the eight children of `next`, then picks (and prefetches) the node to visit after it.
     template <class Stack>
     RPT_D void visit_node(const WideScene& s, Stack& stack) {
+        const Visit v = test_children(s);
+        select_next(s, stack, v);
+    }
+    // The two halves of a visit, for callers that want to put something between them (the extend kernel issues the
+    // loads of the visit's first triangle there): the box tests, which leave the visit's triangle group in the cursor ...
+    struct Visit {
+        uint32_t child_base, imask, hits;  // first child node, inner-slot mask, RPT_CHILD_HIT_BITS of the children hit
+    };
+    RPT_D Visit test_children(const WideScene& s) {
         const uint4* node = s.nodes + 5u * (size_t)next;
 #if RPT_NODE_INDEXED_LOADS && defined(__CUDACC__)
         const uint4 n0 = __ldg(node), n1 = __ldg(node + 1);
@@ -277,11 +289,23 @@ struct WideCursor {
         // de-quantisation into the addend rounds it at magnitude 1024 |adj|, i.e. by < 2^-14 |adj|: 512 more
         // cells in the same pad term cover that four times over.  (RPT_PLANES_FP32: bias 32768, rounded by < 2^-9 |adj|: kPadCells.)
         const f3 rel_o = p - ray.o;
+        const f3 org = rel_o * ray.idir;
+#if RPT_NODE_SHORT_PAD
+        // the same pad from the products that exist anyway, (kPadCells |adj| + |org|) * 6e-7 (the two differ by the
+        // rounding of org and adj, 2^-24 relative, far below the 5/3 margin of the pad), and the biased addend built once:
+        // base -+ pad rounds twice at magnitude <= 1024 |adj| + |org| where the form below rounds once — 2^-13 |adj| of the
+        // 2^-11.7 |adj| (512 cells * 6e-7) set aside for it.  Six instructions fewer per visit.
+        const f3 apad = mk3(fmaf(kPadCells, fabsf(adj.x), fabsf(org.x)) * 6e-7f, fmaf(kPadCells, fabsf(adj.y), fabsf(org.y)) * 6e-7f,
+                            fmaf(kPadCells, fabsf(adj.z), fabsf(org.z)) * 6e-7f);
+        const f3 base = mk3(fmaf(adj.x, -kPlaneBias, org.x), fmaf(adj.y, -kPlaneBias, org.y), fmaf(adj.z, -kPlaneBias, org.z));
+        const f3 org_near = base - apad;
+        const f3 org_far = base + apad;
+#else
         const f3 apad = mk3(fabsf(fmaf(kPadCells, cell.x, fabsf(rel_o.x)) * ray.idir.x) * 6e-7f, fabsf(fmaf(kPadCells, cell.y, fabsf(rel_o.y)) * ray.idir.y) * 6e-7f,
                             fabsf(fmaf(kPadCells, cell.z, fabsf(rel_o.z)) * ray.idir.z) * 6e-7f);
-        const f3 org = rel_o * ray.idir;
         const f3 org_near = mk3(fmaf(adj.x, -kPlaneBias, org.x - apad.x), fmaf(adj.y, -kPlaneBias, org.y - apad.y), fmaf(adj.z, -kPlaneBias, org.z - apad.z));
         const f3 org_far = mk3(fmaf(adj.x, -kPlaneBias, org.x + apad.x), fmaf(adj.y, -kPlaneBias, org.y + apad.y), fmaf(adj.z, -kPlaneBias, org.z + apad.z));
+#endif
 
 #if RPT_NODE_INDEXED_LOADS && defined(__CUDACC__)
         uint32_t h = test_four<0u>(s.half_1024_bytes, near_wx.x, near_wy.x, near_wz.x, far_wx.x, far_wy.x, far_wz.x, adj, org_near, org_far, best_t);
@@ -298,15 +322,19 @@ struct WideCursor {
         tgroup.x = n1.y;
         tvalid = n1.z & 0x00FFFFFFu;
         tgroup.y = h & tvalid;
-
-        // ---- the node after this one: its nearest hit child, else the nearest pending sibling, else the stack
+        return Visit{n1.x, imask, h};
+    }
+    // ... and the choice of the node after this one: its nearest hit child, else the nearest pending sibling, else the stack
+    template <class Stack>
+    RPT_D void select_next(const WideScene& s, Stack& stack, const Visit& v) {
+        const uint32_t imask = v.imask, h = v.hits;
         const uint32_t child_hits = stack.permute(ray.oct_inv, (h >> 24) & imask) << 24;
 #if !defined(__CUDACC__)
         last_child_hits = child_hits;
 #endif
         if (child_hits != 0u) {
             if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
-            ngroup = make_uint2(n1.x, child_hits | imask);
+            ngroup = make_uint2(v.child_base, child_hits | imask);
         } else if (ngroup.y <= 0x00FFFFFFu && !stack.empty()) {
             ngroup = stack.pop();
         }
@@ -339,10 +367,24 @@ struct WideCursor {
     RPT_D bool test_one(const WideScene& s, uint32_t ti) {
         const float4* rec = s.tri_pos + 3u * (size_t)ti;
         const float4 a = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
+        return test_record<ORDER_FREE>(ti, a, e1, e2, true);
+    }
+    // The first pending triangle of the visit: which one it is (wide index; 0 — some valid record — when there is
+    // none), removed from the group.  For callers that load the record themselves and then call test_record.
+    RPT_D uint32_t take_first_triangle(bool& any) {
+        any = tgroup.y != 0u;
+        const int k = highest_bit(tgroup.y | 1u);
+        const uint32_t ti = tgroup.x + (uint32_t)popcount(tvalid & ~(0xFFFFFFFFu << k));
+        tgroup.y &= ~(1u << k);  // (k = 0 when there is none: clearing bit 0 of an empty group changes nothing)
+        return any ? ti : 0u;
+    }
+    // The test proper on a record that is already in registers; `enabled` = false discards the result.
+    template <bool ORDER_FREE>
+    RPT_D bool test_record(uint32_t ti, float4 a, float4 e1, float4 e2, bool enabled) {
         float t;
         bool back;
         // accept 0.001 < t < best so far (nearest) resp. t <= max_t and t < 1e6 (any), intersection.rs:195
-        if (ray_triangle(ray.o, ray.d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t, back) && t > 0.001f &&
+        if (ray_triangle(ray.o, ray.d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t, back) && enabled && t > 0.001f &&
             (NEAREST ? (t < best_t || (ORDER_FREE && t == best_t && hit_tri != kNoNode && ti < (hit_tri & 0x7FFFFFFFu))) : (t <= best_t && t < 1000000.0f))) {
             hit_t = t;
             hit_tri = ti | (back ? 0x80000000u : 0u);

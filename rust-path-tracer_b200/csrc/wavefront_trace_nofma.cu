@@ -16,6 +16,20 @@
 
 namespace rpt {
 
+// RPT_TRACE_STEPWISE (build switch, measured, off): every lane takes ONE step per round — a pending triangle or the next
+// node — instead of "a node, then all of its triangles while the other lanes wait" (DESIGN.md section 4.1).
+#ifndef RPT_TRACE_STEPWISE
+#define RPT_TRACE_STEPWISE 0
+#endif
+#ifndef RPT_TRACE_LATE_WRITE
+#define RPT_TRACE_LATE_WRITE 1
+#endif
+#ifndef RPT_TRI_FIRST_INLINE
+#define RPT_TRI_FIRST_INLINE 0
+#endif
+#ifndef RPT_TRACE_MIN_BLOCKS
+#define RPT_TRACE_MIN_BLOCKS 9  // resident blocks per SM the register allocation aims at: 9 x 128 threads x 56 registers
+#endif
 constexpr int kTraceBlock = 128;  // 4 warps; 16 KB of stack slabs + the 2 KB permutation table per block
 constexpr int kTraceWarps = kTraceBlock / 32;
 size_t trace_stack_overflow_entries(int grid_blocks) { return (size_t)grid_blocks * kTraceBlock * (kWideStackCapacity - kWideStackShared); }
@@ -81,7 +95,7 @@ constexpr uint32_t kMissRecord = 0xFFFFFFFFu;  // hit[].y of a ray that hit noth
 // tests of the launch — the kernel's work in ITS OWN layout (80 B per node, 48 B per triangle record) — into
 // counters[4..7]; the product launches STATS = false.
 template <bool NEAREST, bool DEEP, bool STATS>
-__global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
+__global__ void __launch_bounds__(kTraceBlock, RPT_TRACE_MIN_BLOCKS) wf_trace_kernel(WideScene bvh, WaveState s, int in_queue, bool identity, uint32_t n_identity,
                                                                int refill_below, uint2* stack_overflow) {
     __shared__ uint2 slabs[kTraceWarps][kWideStackShared][32];
     __shared__ uint8_t perm_table[8 * 256];
@@ -101,8 +115,30 @@ __global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh,
     bool busy = false;       // this lane holds an unfinished ray
     bool exhausted = false;  // the cursor ran past the end of the queue (warp-uniform)
     uint32_t stat_visits = 0, stat_tests = 0;
+    // RPT_TRACE_LATE_WRITE: a ray's result is written when the warp next reconverges (every lane that ended since then
+    // writes together) instead of by each lane alone at the moment its ray ends.
+    bool unwritten = false;
+    auto write_result = [&] {
+        if (NEAREST) {  // every traced slot gets a record; kMissRecord marks "no hit" for wf_compact_kernel
+            s.hit[item] = make_uint2(__float_as_uint(c.best_t), c.hit_tri);  // kMissRecord == kNoNode marks "no hit"
+        } else if (c.hit_tri == kNoNode) {  // unoccluded: radiance += mask_nan(contribution) (lib.rs:164; masked when queued)
+            const uint32_t slot = __float_as_uint(s.sh_d[item].w);
+            const float4 add = s.sh_c[item];
+            float4 r = s.rad[slot];
+            r.x += add.x; r.y += add.y; r.z += add.z;
+            s.rad[slot] = r;
+        }
+    };
 
     for (;;) {
+#if RPT_TRACE_LATE_WRITE
+        // ---- converged: the results of the rays that ended since the warp was last here ------------
+        __syncwarp();
+        if (unwritten) {
+            unwritten = false;
+            write_result();
+        }
+#endif
         // ---- converged: refill idle lanes -------------------------------------------------------
         if (!exhausted) {
             const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !busy);
@@ -140,26 +176,52 @@ __global__ void __launch_bounds__(kTraceBlock, 9) wf_trace_kernel(WideScene bvh,
         // ---- traverse until the ray ends or the warp wants a refill ---------------------------
         while (busy) {
             bool finished = false;
-            if (c.has_nodes()) {  // (only a non-finite ray starts without nodes)
+#if RPT_TRACE_STEPWISE
+            // one step per lane per round: a pending triangle if there is one, else the next node — the same per-ray
+            // sequence of visits and tests, so the same result; no lane waits for another lane's triangles
+            if (c.has_triangles()) {
+                if (STATS) ++stat_tests;
+                if (c.test_triangle(bvh)) finished = true;
+            } else if (c.has_nodes()) {
                 c.visit_node(bvh, st);
                 if (STATS) ++stat_visits;
             }
-            while (c.has_triangles()) {
+            if (!c.has_nodes() && !c.has_triangles()) finished = true;
+#else
+            if (c.has_nodes()) {  // (only a non-finite ray starts without nodes)
+                // RPT_TRI_FIRST_INLINE (1: both ray kinds, 2: nearest-hit rays only)
+                constexpr bool kInlineFirst = RPT_TRI_FIRST_INLINE == 1 || (RPT_TRI_FIRST_INLINE == 2 && NEAREST);
+                if constexpr (kInlineFirst) {
+                    // The visit's first triangle is tested as part of the visit, by every lane of the node block (a lane
+                    // whose visit found none tests record 0 and discards the result): with ~26 lanes visiting, some lane
+                    // has one in practically every round, so the triangle block ran once per round anyway — this way its
+                    // loads are issued before the next-node selection instead of after it, and the first test needs no branch.
+                    const typename WideCursor<NEAREST>::Visit v = c.test_children(bvh);
+                    bool any;
+                    const uint32_t ti = c.take_first_triangle(any);
+                    const float4* rec = bvh.tri_pos + 3u * (size_t)ti;
+                    const float4 ta = __ldg(rec), te1 = __ldg(rec + 1), te2 = __ldg(rec + 2);
+                    c.select_next(bvh, st, v);
+                    if (STATS) { ++stat_visits; stat_tests += any ? 1u : 0u; }
+                    if (c.template test_record<false>(ti, ta, te1, te2, any)) finished = true;
+                } else {
+                    c.visit_node(bvh, st);
+                    if (STATS) ++stat_visits;
+                }
+            }
+            while (!finished && c.has_triangles()) {
                 if (STATS) ++stat_tests;
                 if (c.test_triangle(bvh)) { finished = true; break; }
             }
             if (!c.has_nodes()) finished = true;
+#endif
             if (finished) {
                 busy = false;
-                if (NEAREST) {  // every traced slot gets a record; kMissRecord marks "no hit" for wf_compact_kernel
-                    s.hit[item] = make_uint2(__float_as_uint(c.best_t), c.hit_tri);  // kMissRecord == kNoNode marks "no hit"
-                } else if (c.hit_tri == kNoNode) {  // unoccluded: radiance += mask_nan(contribution) (lib.rs:164; masked when queued)
-                    const uint32_t slot = __float_as_uint(s.sh_d[item].w);
-                    const float4 add = s.sh_c[item];
-                    float4 r = s.rad[slot];
-                    r.x += add.x; r.y += add.y; r.z += add.z;
-                    s.rad[slot] = r;
-                }
+#if RPT_TRACE_LATE_WRITE
+                unwritten = true;
+#else
+                write_result();
+#endif
                 break;
             }
             if (!exhausted && __popc(__activemask()) < refill_below) break;

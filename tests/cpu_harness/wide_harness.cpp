@@ -366,4 +366,76 @@ int harness_warp_sim2(const RptPerVertexData* verts, uint32_t nverts, const uint
     out[0] = node_rounds; out[1] = lane_visits; out[2] = tri_rounds; out[3] = lane_tests; out[4] = nrays; out[5] = refills;
     return 0;
 }
+
+// Experiment 3 (round 2): ONE STEP PER LANE PER ROUND.  In every round a lane tests one pending triangle if it has one
+// and visits its next node otherwise; the warp runs the triangle block (for the lanes that chose it) and the node
+// block (for the others) once each.  A lane never waits for another lane's triangles, and every ray performs exactly
+// the per-ray sequence of the plain loop (visit, that visit's triangles, next visit), so results and visit counts are
+// unchanged; what changes is that the triangle block runs once per round for every lane that currently holds a
+// triangle, instead of max-over-lanes times per node round for the few lanes that found one in THAT round.
+//   tri_min: the triangle block only runs when at least that many lanes want it or no lane wants a node (lanes that
+//            want a triangle idle through the round otherwise); 1 = always.
+// out as harness_warp_sim.
+int harness_warp_sim3(const RptPerVertexData* verts, uint32_t nverts, const uint32_t* tris, uint32_t ntris, const RptBVHNode* nodes, uint32_t nnodes,
+                      const float* rays_o_d, uint32_t nrays, int refill_below, int tri_min, uint64_t* out) {
+    rpt::WideBvh wide;
+    const char* err = "";
+    if (!rpt::build_wide_bvh(nodes, nnodes, tris, ntris, verts, nverts, wide, &err)) return -1;
+    rpt::WideScene scene{reinterpret_cast<const rpt::uint4*>(wide.nodes.data()), reinterpret_cast<const rpt::float4*>(wide.tri_pos.data()), rpt::kHalf1024Bytes};
+    struct Lane {
+        rpt::WideCursor<true> c;
+        LocalStack st;
+        bool busy = false;
+        uint32_t ray = 0;
+    };
+    std::vector<Lane> lanes(32);
+    uint64_t node_rounds = 0, lane_visits = 0, tri_rounds = 0, lane_tests = 0, refills = 0, wrong = 0;
+    uint32_t fetch = 0;
+    auto live = [&] { int n = 0; for (const Lane& l : lanes) n += l.busy; return n; };
+    for (;;) {
+        if (fetch < nrays && live() < refill_below) {
+            ++refills;
+            for (Lane& l : lanes) {
+                if (l.busy || fetch >= nrays) continue;
+                l.ray = fetch;
+                const float* r = rays_o_d + 6 * (size_t)fetch++;
+                l.c.begin(rpt::mk3(r[0], r[1], r[2]), rpt::mk3(r[3], r[4], r[5]), 0.0f);
+                l.st.clear();
+                l.busy = true;
+            }
+        }
+        if (live() == 0) break;
+        int want_tri = 0, want_node = 0;
+        for (const Lane& l : lanes) {
+            if (!l.busy) continue;
+            if (l.c.has_triangles()) ++want_tri;
+            else if (l.c.has_nodes()) ++want_node;
+        }
+        const bool run_tri = want_tri > 0 && (want_tri >= tri_min || want_node == 0);
+        int testing = 0, visiting = 0;
+        for (Lane& l : lanes) {
+            if (!l.busy) continue;
+            if (l.c.has_triangles()) {
+                if (run_tri) { l.c.test_triangle(scene); ++testing; }
+            } else if (l.c.has_nodes()) {
+                l.c.visit_node(scene, l.st);
+                ++visiting;
+            }
+        }
+        if (testing) { ++tri_rounds; lane_tests += (uint64_t)testing; }
+        if (visiting) { ++node_rounds; lane_visits += (uint64_t)visiting; }
+        for (Lane& l : lanes)
+            if (l.busy && !l.c.has_nodes() && !l.c.has_triangles()) {
+                l.busy = false;
+                const float* r = rays_o_d + 6 * (size_t)l.ray;
+                LocalStack st;
+                const rpt::WideHit want = rpt::wide_intersect<true>(scene, rpt::mk3(r[0], r[1], r[2]), rpt::mk3(r[3], r[4], r[5]), 0.0f, st);
+                const rpt::WideHit got = l.c.result();
+                if (got.hit != want.hit || (got.hit && (got.triangle != want.triangle || std::memcmp(&got.t, &want.t, 4) != 0 || got.backface != want.backface))) ++wrong;
+            }
+    }
+    out[6] = wrong;
+    out[0] = node_rounds; out[1] = lane_visits; out[2] = tri_rounds; out[3] = lane_tests; out[4] = nrays; out[5] = refills;
+    return 0;
+}
 }

@@ -49,7 +49,27 @@ def sim2(world, rays, refill_below, t_hi, t_lo, capacity, blocked_at=99):
             "tests/ray": lt / n, "instr/ray": (nr * (NODE_INSTR + 12) + tr * (TRI_INSTR + 8)) / n, "wrong": float(out[6]), "forced": float(out[7]) / n}
 
 
+def sim3(world, rays, refill_below, tri_min):
+    out = np.zeros(8, np.uint64)
+    rc = lib.harness_warp_sim3(P(world.per_vertex_buffer), C.c_uint32(len(world.per_vertex_buffer)), P(world.index_buffer), C.c_uint32(len(world.index_buffer)),
+                               P(world.nodes), C.c_uint32(len(world.nodes)), P(rays), C.c_uint32(len(rays)), C.c_int(refill_below), C.c_int(tri_min), P(out))
+    assert rc == 0 and out[6] == 0, (rc, out)
+    nr, lv, tr, lt, n = (float(x) for x in out[:5])
+    return {"node_rounds/ray": nr / n, "lanes/node_round": lv / nr, "visits/ray": lv / n, "tri_rounds/ray": tr / n, "lanes/tri_round": lt / max(tr, 1),
+            "tests/ray": lt / n, "instr/ray": (nr * NODE_INSTR + tr * TRI_INSTR) / n}
+
+
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64000
+if len(sys.argv) > 2 and sys.argv[2] == "step":
+    for name in ("breaktime", "cornell"):
+        world = bench.load_workload(name)[0]
+        rays = surface_rays(world, n)
+        r = sim(world, rays, 20, 0, 0)
+        print(f"{name:10s} as built:              " + "  ".join(f"{k} {v:7.3f}" for k, v in r.items()), flush=True)
+        for refill, tri_min in ((20, 1), (24, 1), (28, 1), (20, 2), (20, 4), (24, 4), (20, 8)):
+            r = sim3(world, rays, refill, tri_min)
+            print(f"{name:10s} one step per round, refill<{refill} tri_min {tri_min}: " + "  ".join(f"{k} {v:7.3f}" for k, v in r.items()), flush=True)
+    sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == "partial":
     for name in ("breaktime", "cornell"):
         world = bench.load_workload(name)[0]
