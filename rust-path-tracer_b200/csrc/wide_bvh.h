@@ -64,7 +64,10 @@ bool build_wide_bvh(const RptBVHNode* nodes, uint32_t nnodes, const uint32_t* tr
 // Traversal stack: the first kWideStackShared entries of a lane live in shared memory (8-wide: a 1M-triangle scene
 // is 10 levels deep), deeper ones in a global-memory overflow area; trees deeper than kWideStackCapacity are
 // rejected at upload.
-constexpr uint32_t kWideStackShared = 12;
+#ifndef RPT_STACK_SHARED
+#define RPT_STACK_SHARED 12
+#endif
+constexpr uint32_t kWideStackShared = RPT_STACK_SHARED;
 constexpr uint32_t kWideStackCapacity = 64;
 
 }  // namespace rpt
