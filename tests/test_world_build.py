@@ -163,6 +163,41 @@ def test_blue_noise_seeds():
     assert y[5, 7] == expect
 
 
+def test_blue_noise_seed_rule_for_every_tile_value():
+    """src/trace.rs:149-160 for all 256 tile values: y = ((px as f32 / 255.0) * 4294967295.0) as u32 — the constant is
+    2^32 as an f32 and `as u32` saturates, so px = 255 gives u32::MAX — evaluated here in numpy float32, independently of
+    the C++ producer."""
+    tile = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    seeds = np.zeros((16 * 16, 2), np.uint32)
+    from rust_path_tracer_b200 import capi
+    import ctypes as C
+
+    capi.check(capi.lib().rpt_make_rng_seeds(capi.ptr(tile), C.c_uint32(16), C.c_uint32(16), C.c_uint32(16), C.c_uint32(16), C.c_uint64(0), capi.ptr(seeds)), "seeds")
+    scaled = (tile.astype(np.float32).ravel() / np.float32(255.0)) * np.float32(4294967295.0)
+    expect = np.minimum(scaled.astype(np.float64), 4294967295.0).astype(np.uint64).astype(np.uint32)  # f32 -> u32, saturating
+    np.testing.assert_array_equal(seeds[:, 1], expect)
+    assert seeds[255, 1] == 0xFFFFFFFF and (seeds[:, 0] == 0).all()
+
+
+def test_sixteen_bit_to_eight_bit_rule_is_the_rounded_rescale():
+    """The tile is a 16-bit gray PNG; `into_rgba8()` (image 0.24, not vendored) narrows it with (c + 128) / 257.  That
+    rule is not arbitrary: for every one of the 65 536 inputs it equals round-half-up of c * 255 / 65535, the exact
+    rescale (checked here in integers), and it inverts the widening c8 * 257.  The older `c >> 8` differs on a quarter of
+    the inputs; the reference's only known answer cannot tell them apart, which is why DESIGN.md lists
+    this rule as restated, not pinned."""
+    c = np.arange(65536, dtype=np.int64)
+    rule = (c + 128) // 257
+    exact = (2 * c * 255 + 65535) // (2 * 65535)  # floor(c * 255 / 65535 + 1/2)
+    np.testing.assert_array_equal(rule, exact)
+    np.testing.assert_array_equal((np.arange(256) * 257 + 128) // 257, np.arange(256))
+    assert 0.2 < ((c >> 8) != rule).mean() < 0.6
+    tile = np.load(helpers.REPO + "/rust-path-tracer_b200/resources/bluenoise_r8.npy")
+    assert tile.shape == (256, 256) and tile.dtype == np.uint8
+    # a blue-noise tile spreads its values evenly: every 8-bit level occurs (257 +- a few) / 65536 of the time
+    hist = np.bincount(tile.ravel(), minlength=256)
+    assert hist.min() > 100 and hist.max() < 400
+
+
 def test_parallel_bvh_build_is_identical_to_the_sequential_one(monkeypatch):
     """The builder forks the big subtrees near the root into tasks and splices their local node arrays; nodes,
     their order and the permutation of the index buffer must not depend on the thread count."""
