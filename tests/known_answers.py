@@ -192,6 +192,68 @@ def mirror_prediction(width, height, albedo, metallic, environment):
     return img
 
 
+@functools.lru_cache(maxsize=None)
+def _rough_specular_table(roughness, f0, n_table=128, n_phi=256, n_r2=1024):
+    """E over (r1, r2) uniform in [0, 1)^2 of the specular lobe's spectrum / pdf as `PBR::sample` computes it with
+    specular_weight = 1, per channel of f0, as a function of cos(theta_v) — float64 numpy straight from the reference's
+    formulas, none of the repo's code:
+      sample_ggx (util.rs:67-85)      l = GGX-distributed direction AROUND THE MIRROR DIRECTION R (a = roughness^2,
+                                      cos = sqrt((1 - r2) / (r2 (a^2 - 1) + 1)), phi = 2 pi r1) — the sampled direction
+                                      itself, not a half vector
+      ggx_distribution (util.rs:58-64) D = r^2 / max(pi ((n.h)^2 (r^2 - 1) + 1)^2, EPS), h = normalize(v + l)
+      geometry (util.rs:211-227)      G = g(n.v) g(n.l), g(x) = max(x, 0) / (max(x, 0) (1 - k) + k), k = r^2 / 8
+      spectrum (bsdf.rs:212-227)      D G F / max(4 max(n.v, 0) c, EPS) * c, c = max(n.l, EPS), F = Schlick(max(h.v, 0), f0)
+      pdf (bsdf.rs:233-241)           D (n.h) / (4 v.h)
+    A sample below the horizon has G = 0 and contributes nothing; every other one leaves the convex sphere."""
+    eps = 1e-3
+    cv = np.linspace(0.05, 1.0, n_table)
+    r1 = (np.arange(n_phi) + 0.5) / n_phi
+    r2 = ((np.arange(n_r2) + 0.5) / n_r2)[:, None]
+    a = roughness * roughness
+    cos_t = np.sqrt((1 - r2) / (r2 * (a * a - 1) + 1))
+    sin_t = np.sqrt(np.maximum(1 - cos_t * cos_t, 0))
+    phi = 2 * np.pi * r1[None, :]
+    k = roughness * roughness / 8
+    g = lambda x: np.maximum(x, 0) / (np.maximum(x, 0) * (1 - k) + k)
+    f0 = np.asarray(f0, np.float64)
+    out = np.empty((n_table, 3))
+    for i, c in enumerate(cv):
+        s_v = np.sqrt(max(0.0, 1 - c * c))
+        v = np.array([s_v, 0.0, c])           # normal = +z
+        refl = np.array([-s_v, 0.0, c])       # reflect(-v, n)
+        t = np.cross([0.0, 1.0, 0.0], refl)   # any frame around R: the lobe is isotropic in phi
+        t /= np.linalg.norm(t)
+        b = np.cross(refl, t)
+        l = (t[None, None, :] * (np.cos(phi) * sin_t)[..., None] + b[None, None, :] * (np.sin(phi) * sin_t)[..., None]
+             + refl[None, None, :] * (cos_t * np.ones_like(phi))[..., None])
+        l /= np.linalg.norm(l, axis=-1, keepdims=True)
+        nl = l[..., 2]
+        h = l + v
+        h /= np.linalg.norm(h, axis=-1, keepdims=True)
+        nh, vh = h[..., 2], h @ v
+        d = roughness ** 2 / np.maximum(np.pi * (np.maximum(nh, 0) ** 2 * (roughness ** 2 - 1) + 1) ** 2, eps)
+        cth = np.maximum(nl, eps)
+        fres = schlick(np.maximum(vh, 0)[..., None], f0[None, None, :])
+        spectrum = (d * g(c) * g(nl))[..., None] * fres / np.maximum(4 * max(c, 0.0) * cth, eps)[..., None] * cth[..., None]
+        pdf = d * nh / (4 * vh)
+        w = np.where((nl > 0)[..., None], spectrum / pdf[..., None], 0.0)
+        out[i] = w.mean((0, 1))
+    return cv, out
+
+
+def rough_metal_prediction(width, height, albedo, roughness, metallic, environment):
+    """Image of the sphere under a constant environment when only the specular lobe exists (specular_weight_clamp =
+    (1, 1)) at a finite roughness: environment * E[spectrum / pdf] by quadrature; NaN outside the sphere's interior
+    and where the view grazes (cos < 0.05)."""
+    cosv = sphere_pixel_cosines(width, height)
+    f0 = tuple(float(x) for x in 0.04 + (np.asarray(albedo, np.float64) - 0.04) * metallic)
+    cv, table = _rough_specular_table(float(roughness), f0)
+    c = np.nan_to_num(cosv, nan=1.0)
+    img = np.stack([environment * np.interp(c, cv, table[:, k]) for k in range(3)], -1)
+    img[np.isnan(cosv) | (c < 0.05)] = np.nan
+    return img
+
+
 def relative_error_of_mean(image, prediction):
     """|mean(image) / mean(prediction) - 1| per channel over the pixels the prediction covers."""
     mask = np.isfinite(prediction).all(-1)
