@@ -154,6 +154,13 @@ struct Rng {
     }
     V2 r2() { float a = r1(); float b = r1(); return {a, b}; }
     V3 r3() { float a = r1(); float b = r1(); float c = r1(); return {a, b, c}; }
+    // (test switch only, see oracle_set_retire_dead_paths) one of the numbers still to be drawn is exactly 1.0:
+    // `u32 as f32` rounds 0xFFFFFF80 and above up to 2^32
+    bool draws_one_ahead() const {
+        for (uint32_t d = dimension + 1; d < 32; ++d)
+            if ((uint32_t)(kLdsPrimes[d] * (n + offset)) >= 0xFFFFFF80u) return true;
+        return false;
+    }
 };
 
 // ------------------------------------------------------------------ intersection.rs
@@ -675,7 +682,7 @@ PixelResult trace_pixel(uint32_t px, uint32_t py, const RptTracingConfig& cfg, u
             float prob = max_element(throughput);
             if (rng.r1() > prob) break;
             throughput = throughput * (1.0f / prob);
-        } else if (g_retire_dead_paths && is_zero(throughput)) {
+        } else if (g_retire_dead_paths && is_zero(throughput) && !rng.draws_one_ahead()) {
             break;  // NOT in the reference: see oracle_set_retire_dead_paths
         }
     }
@@ -700,7 +707,11 @@ extern "C" {
 // Checker for one optimisation of the CUDA backend (wavefront_shade.cu retires paths whose throughput is exactly zero):
 // with the switch on, the restatement stops such paths too, so tests can show on the CPU — at sizes and on scenes the
 // GPU tests do not cover — that the accumulator does not change in a single bit.  Off by default: the reference
-// walks those paths to their first roulette bounce.
+// walks those paths to their first roulette bounce.  The backend's rule has one guard, restated here with it: a dead
+// path that can still draw a random number of exactly 1.0 is NOT retired — a lobe selector of 1.0 meeting a specular
+// weight of 1.0 gives the diffuse term 1 / (1 - 1) = inf (bsdf.rs:202-211), 0 x inf = NaN, and the NaN then reaches the
+// accumulator through the unmasked sky term (lib.rs:69): found on the BreakTime proxy at sample 4534, where 4 of the
+// reference's 20 NaN pixels are such paths (tests/test_dead_paths_cpu.py).
 void oracle_set_retire_dead_paths(int on) { g_retire_dead_paths = on != 0; }
 
 struct OracleWorld {

@@ -32,6 +32,12 @@ struct Rng {
         // `u32 as f32` rounds to nearest even; can produce exactly 1.0 (rng.rs:31)
         return (float)(c_lds_primes[dim & 31u] * key) * (1.0f / 4294967296.0f);
     }
+    // One of the numbers this path can still draw is exactly 1.0 (`u32 as f32` rounds 0xFFFFFF80 and above up to 2^32).
+    RPT_D bool draws_one_ahead() const {
+        for (uint32_t d = dim + 1u; d < 32u; ++d)
+            if (c_lds_primes[d] * key >= 0xFFFFFF80u) return true;
+        return false;
+    }
 };
 
 // ---- camera ray, kernels/src/lib.rs:38-51 -------------------------------------------------

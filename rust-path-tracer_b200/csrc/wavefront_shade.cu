@@ -192,10 +192,14 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) wf_shade_kernel(
                     roulette = max_element(next_thr);
                     if (rstate.next() > roulette) want_next = false;
                     next_thr = next_thr * (1.0f / roulette);
-                } else if (f.retire_dead_paths && zero3(next_thr)) {
+                } else if (f.retire_dead_paths && zero3(next_thr) && !rstate.draws_one_ahead()) {
                     // Throughput exactly zero before the roulette bounces (a specular sample under the horizon, a black
                     // texel): everything the rest of this path can add is 0 x (something finite) — the reference walks
                     // it to its first roulette, which ends it.  5-17 % of all path vertices on the scenes here.
+                    // "Finite" has one exception that random numbers alone produce, hence the guard: a lobe selector of
+                    // exactly 1.0 against a specular weight of exactly 1.0 picks the diffuse lobe with 1 / (1 - 1) = inf,
+                    // 0 x inf = NaN, and the unmasked sky term carries the NaN into the accumulator (4 of the reference's
+                    // 20 NaN pixels of the proxy at sample 4534).  Such a path is traced on, like the reference does.
                     want_next = false;
                 }
                 if (want_next) {

@@ -702,6 +702,27 @@ def test_bench_workload_breaktime_proxy_at_full_size():
     _full_size_case("breaktime", 2, "BreakTime proxy 1M tris 1920x1080 2spp MIS (bench workload, full size)")
 
 
+def test_nan_samples_of_the_cpu_path_are_nan_here_too():
+    """Sample 4534 of the bench workload's frame (found by tools/gpu_nan_hunt.py over 5120 samples per pixel): a random
+    number of exactly 1.0 gives the reference 20 NaN pixels, four of them on paths whose throughput was already zero
+    (tests/test_dead_paths_cpu.py).  The retirement rule's guard keeps those four alive: the same pixels are NaN here."""
+    import bench
+
+    world, cfg, seeds, _spp, _label, _scene, sky = bench.load_workload("breaktime")
+    at = seeds.copy()
+    at[:, 0] += np.uint32(4534)
+    o_out = render_oracle(world, cfg, at, 1, sky)[0]
+    c_out = render_cuda(world, cfg, at, 1, capi.PIPELINE_WAVEFRONT, sky)[0]
+    nan_oracle = np.flatnonzero(~np.isfinite(o_out[:, :3]).all(axis=1))
+    nan_cuda = np.flatnonzero(~np.isfinite(c_out[:, :3]).all(axis=1))
+    err, _bad = helpers.mae(c_out[:, :3], o_out[:, :3])
+    helpers.record_parity("BreakTime proxy 1920x1080, sample index 4534 alone (a random number of exactly 1.0)", nan_pixels_cuda=int(len(nan_cuda)),
+                          nan_pixels_oracle=int(len(nan_oracle)), same_pixels=bool(np.array_equal(nan_cuda, nan_oracle)), mae=err)
+    assert len(nan_oracle) == 20
+    np.testing.assert_array_equal(nan_cuda, nan_oracle)
+    assert err <= MAE_TOLERANCE
+
+
 def test_config2_pbrtest_at_full_size():
     """configs[2]: PBRTest 1920x1080, procedural sky (every path ends in `scatter`), 2 of its 512 samples."""
     _full_size_case("pbr", 2, "PBRTest 1920x1080 2spp procedural sky (configs[2] frame)")
