@@ -1,6 +1,6 @@
 """Scratch diagnostics on the GPU box: primary ids of both pipelines vs the oracle."""
 import os, sys
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (REPO, REPO + "/oracle", REPO + "/tests"):
     sys.path.insert(0, p)
 import numpy as np

@@ -1,6 +1,6 @@
 """Scratch: MAE of the wavefront pipeline against the oracle on the HDR stress cases (run on the GPU box)."""
 import os, sys
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests")); sys.path.insert(0, os.path.join(REPO, "oracle"))
 import numpy as np
 import helpers

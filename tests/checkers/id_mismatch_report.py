@@ -1,9 +1,9 @@
 """What ARE the primary-hit id mismatches at full size?  Runs on the CPU: the oracle's traversal of the reference BVH and
 the product's wide-BVH traversal (host build of the same code, tests/cpu_harness) on the primary rays of sample 0 of
 the benchmarked frame, then looks at every pixel where the two name different triangles.
-usage: python tools/id_mismatch_report.py [workload]      (writes profiles/r2_id_mismatches.txt)"""
+usage: python tests/checkers/id_mismatch_report.py [workload]      (writes profiles/r2_id_mismatches.txt)"""
 import os, sys
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (REPO, os.path.join(REPO, "oracle"), os.path.join(REPO, "tests")):
     sys.path.insert(0, p)
 import numpy as np

@@ -1,6 +1,6 @@
 """Generate the committed golden vectors under tests/golden/ by running the CPU oracle.
 
-    python tools/make_golden.py
+    python tests/checkers/make_golden.py
 
 Each .npz holds, for one small case: the accumulator after `spp` samples (float32 sum rgb + count),
 the bounce-0 triangle ids of sample 0, and the oracle's ray counters.  tests/test_golden.py checks
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (REPO, os.path.join(REPO, "oracle"), os.path.join(REPO, "tests")):
     sys.path.insert(0, p)
 import helpers  # noqa: E402

@@ -1,7 +1,7 @@
 """CPU side of tools/gpu_nan_hunt.py: render exactly the sample indices the GPU found NaN with the oracle and compare,
-pixel by pixel, which are NaN there.  usage: python tools/nan_samples_vs_oracle.py [gpurun_out/nan_samples.json]"""
+pixel by pixel, which are NaN there.  usage: python tests/checkers/nan_samples_vs_oracle.py [gpurun_out/nan_samples.json]"""
 import json, os, sys
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "oracle"))
 import numpy as np
 import bench

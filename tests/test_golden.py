@@ -1,4 +1,4 @@
-"""The oracle reproduces the committed golden vectors bit for bit (tools/make_golden.py made them);
+"""The oracle reproduces the committed golden vectors bit for bit (tests/checkers/make_golden.py made them);
 this guards the checker itself against drift between rounds."""
 import glob
 import os

@@ -2,7 +2,7 @@
 (kernels/src/lib.rs:69), so a pixel whose sample k is NaN stays NaN for good; at thousands of samples per pixel a
 handful of pixels of the BreakTime proxy are (bench.py's reduce_check counts 16 at 5120 spp).  This finds, for every such
 pixel, the FIRST sample index that is NaN (chunks of `chunk` samples, then the chunk again one sample at a time), and
-writes the list to gpurun_out/nan_samples.json — tools/nan_samples_vs_oracle.py then asks the CPU oracle for exactly
+writes the list to gpurun_out/nan_samples.json — tests/checkers/nan_samples_vs_oracle.py then asks the CPU oracle for exactly
 those samples.
 usage: python tools/gpu_nan_hunt.py [workload] [total_spp] [chunk]"""
 import json, os, sys
