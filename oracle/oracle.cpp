@@ -156,8 +156,9 @@ struct Rng {
     V3 r3() { float a = r1(); float b = r1(); float c = r1(); return {a, b, c}; }
     // (test switch only, see oracle_set_retire_dead_paths) one of the numbers still to be drawn is exactly 1.0:
     // `u32 as f32` rounds 0xFFFFFF80 and above up to 2^32
-    bool draws_one_ahead() const {
-        for (uint32_t d = dimension + 1; d < 32; ++d)
+    // (all 31 dimensions, drawn or not — the backend's form of the guard, which is cheaper to evaluate that way)
+    bool draws_a_one() const {
+        for (uint32_t d = 1; d < 32; ++d)
             if ((uint32_t)(kLdsPrimes[d] * (n + offset)) >= 0xFFFFFF80u) return true;
         return false;
     }
@@ -682,7 +683,7 @@ PixelResult trace_pixel(uint32_t px, uint32_t py, const RptTracingConfig& cfg, u
             float prob = max_element(throughput);
             if (rng.r1() > prob) break;
             throughput = throughput * (1.0f / prob);
-        } else if (g_retire_dead_paths && is_zero(throughput) && !rng.draws_one_ahead()) {
+        } else if (g_retire_dead_paths && is_zero(throughput) && !rng.draws_a_one()) {
             break;  // NOT in the reference: see oracle_set_retire_dead_paths
         }
     }

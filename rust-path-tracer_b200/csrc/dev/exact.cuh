@@ -32,11 +32,21 @@ struct Rng {
         // `u32 as f32` rounds to nearest even; can produce exactly 1.0 (rng.rs:31)
         return (float)(c_lds_primes[dim & 31u] * key) * (1.0f / 4294967296.0f);
     }
-    // One of the numbers this path can still draw is exactly 1.0 (`u32 as f32` rounds 0xFFFFFF80 and above up to 2^32).
-    RPT_D bool draws_one_ahead() const {
-        for (uint32_t d = dim + 1u; d < 32u; ++d)
-            if (c_lds_primes[d] * key >= 0xFFFFFF80u) return true;
-        return false;
+    // One of the numbers this path draws is exactly 1.0: `u32 as f32` rounds 0xFFFFFF80 and above up to 2^32, i.e. the
+    // NEGATED product PRIME[d] * (-key) mod 2^32 is at most 128 (0 — the number 0.0 — is let through as well: harmless).
+    // All 31 dimensions, drawn or not, so that the loop unrolls into one multiply per dimension (the prime is a
+    // constant-bank operand) and half a three-input minimum; ~50 instructions for the lanes that ask.
+    RPT_D bool draws_a_one() const {
+        const uint32_t negated = 0u - key;
+        uint32_t least = 0xFFFFFFFFu;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (uint32_t d = 1u; d < 32u; ++d) {
+            const uint32_t q = c_lds_primes[d] * negated;
+            least = q < least ? q : least;
+        }
+        return least <= 128u;
     }
 };
 

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) wf_shade_kernel(
                     roulette = max_element(next_thr);
                     if (rstate.next() > roulette) want_next = false;
                     next_thr = next_thr * (1.0f / roulette);
-                } else if (f.retire_dead_paths && zero3(next_thr) && !rstate.draws_one_ahead()) {
+                } else if (f.retire_dead_paths && zero3(next_thr) && !rstate.draws_a_one()) {
                     // Throughput exactly zero before the roulette bounces (a specular sample under the horizon, a black
                     // texel): everything the rest of this path can add is 0 x (something finite) — the reference walks
                     // it to its first roulette, which ends it.  5-17 % of all path vertices on the scenes here.
