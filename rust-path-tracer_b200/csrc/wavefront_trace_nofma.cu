@@ -16,8 +16,16 @@
 
 namespace rpt {
 
-// RPT_TRACE_STEPWISE (build switch, measured, off): every lane takes ONE step per round — a pending triangle or the next
-// node — instead of "a node, then all of its triangles while the other lanes wait" (DESIGN.md section 4.1).
+// Build switches of the trace kernels; every one was measured on a B200 (profiles/r2_variant_sweeps.txt):
+//   RPT_TRACE_LATE_WRITE   ON   a finished ray's result is written when the warp next reconverges, by all lanes that ended
+//                               since then together, instead of by one lane alone (shadow-connect -5 %, extend -1 %)
+//   RPT_TRACE_STEPWISE     off  every lane takes ONE step per round — a pending triangle or the next node — instead of "a
+//                               node, then all of its triangles while the other lanes wait" (a wash / -10 % on DarkCornell)
+//   RPT_TRI_FIRST_INLINE   off  the first triangle of a visit tested inside the node block (1: both ray kinds, 2: nearest
+//                               only): extend +6 %
+//   RPT_TRACE_MIN_BLOCKS   9    resident blocks per SM the register allocation aims at (8: -3 %, 10: -6 %)
+// (dev/exact.cuh: RPT_TRI_STRAIGHT, ON; dev/wide_bvh.cuh: RPT_NODE_SHORT_PAD, ON, RPT_PLANES_FP32 / RPT_NODE_INDEXED_LOADS, off;
+// wide_bvh.h: RPT_STACK_SHARED, 12.)
 #ifndef RPT_TRACE_STEPWISE
 #define RPT_TRACE_STEPWISE 0
 #endif
