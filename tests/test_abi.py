@@ -96,3 +96,17 @@ def test_staging_block_outlives_the_array_it_was_made_for():
     del view
     gc.collect()
     assert freed
+
+
+def test_integration_doc_binds_every_declared_symbol():
+    """INTEGRATION.md shows the Rust `extern "C"` block a maintainer of the reference would add: it has to name every
+    function include/*.h declares (and nothing the library does not export)."""
+    import helpers
+
+    declared = set()
+    for header in ("rpt_b200.h", "rpt_host.h"):
+        text = open(os.path.join(helpers.REPO, "include", header)).read()
+        declared |= set(re.findall(r"^(?:int|const char\*) (rpt_[a-z0-9_]+)\(", text, flags=re.M))
+    bound = set(re.findall(r"pub fn (rpt_[a-z0-9_]+)\(", open(os.path.join(helpers.REPO, "INTEGRATION.md")).read()))
+    assert declared and declared <= bound, sorted(declared - bound)
+    assert bound <= set(capi.HOST_SYMBOLS + capi.DEVICE_SYMBOLS), sorted(bound - set(capi.HOST_SYMBOLS + capi.DEVICE_SYMBOLS))
