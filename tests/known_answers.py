@@ -113,6 +113,88 @@ def flat_normal_map_sphere_world():
     return World.from_baked(scene, atlas=atlas)
 
 
+@functools.lru_cache(maxsize=None)
+def gradient_albedo_sphere_world():
+    """The sphere with a smooth, non-constant albedo texture through the atlas (red rises with x, green with y of the
+    texture) — what a constant texture cannot show: uv interpolation (H1), the rect mapping and the bilinear polyfill on
+    RGBA8 texels (H3).  Returns the world (its atlas is what the prediction reads)."""
+    from rust_path_tracer_b200.atlas import pack_scene_textures
+    from rust_path_tracer_b200.world import World
+
+    base = _furnace_baked()
+    n = 64
+    ramp = np.linspace(40, 250, n).astype(np.uint8)
+    img = np.empty((n, n, 4), np.uint8)
+    img[..., 0] = ramp[None, :]
+    img[..., 1] = ramp[:, None]
+    img[..., 2] = 128
+    img[..., 3] = 255
+    tex = [dict() for _ in base.materials]
+    tex[0] = {"albedo": img}
+    scene = _clone(base, indices=base.indices[base.indices[:, 3] == 0].copy(), textures=tex)
+    scene.uvs = (0.25 + 0.5 * (base.uvs - np.floor(base.uvs))).astype(np.float32)
+    atlas = pack_scene_textures(scene, 256, 256)
+    return World.from_baked(scene, atlas=atlas)
+
+
+def albedo_texture_prediction(world, width, height, cam=(0.0, 1.0, -5.0)):
+    """Albedo the reference's lookup yields at every pixel-centre primary hit, float64 numpy straight from the scene
+    buffers: brute-force nearest triangle, barycentrics of the hit point (util.rs:238-251), uv interpolation
+    (lib.rs:119-129, out-of-range uvs wrapped by fract), the material's rect (bsdf.rs:356) and the CPU polyfill's bilinear
+    with floor / ceil taps and modulo wrap on texels / 255 (image_polyfill.rs:32-55).  NaN where the ray misses."""
+    ys, xs = np.mgrid[0:height, 0:width]
+    u = ((xs + 0.5) / width) * 2 - 1
+    v = ((1 - (ys + 0.5) / height) * 2 - 1) * (height / width)
+    d = np.stack([u, v, np.ones_like(u)], -1).reshape(-1, 3)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = np.asarray(cam, np.float64)
+    pos = world.per_vertex_buffer["vertex"][:, :3].astype(np.float64)
+    uvs = np.stack([world.per_vertex_buffer["uv0"][:, 0], world.per_vertex_buffer["uv0"][:, 1]], 1).astype(np.float64) if "uv0" in world.per_vertex_buffer.dtype.names else None
+    tri = world.index_buffer[:, :3]
+    best_t = np.full(len(d), np.inf)
+    best = np.full(len(d), -1)
+    for i in range(len(tri)):
+        a, e1, e2 = pos[tri[i, 0]], pos[tri[i, 1]] - pos[tri[i, 0]], pos[tri[i, 2]] - pos[tri[i, 0]]
+        pv = np.cross(d, e2)
+        det = pv @ e1
+        ok = np.abs(det) >= 1e-6
+        inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+        tv = o - a
+        uu = (pv @ tv) * inv
+        qv = np.cross(tv, e1)
+        vv = (d @ qv) * inv
+        t = (qv @ e2) * inv
+        hit = ok & (uu >= 0) & (uu <= 1) & (vv >= 0) & (uu + vv <= 1) & (t > 0.001) & (t < best_t)
+        best_t = np.where(hit, t, best_t)
+        best[hit] = i
+    hitmask = best >= 0
+    p = o + d * np.where(hitmask, best_t, 0.0)[:, None]
+    ia, ib, ic = (tri[np.maximum(best, 0), k] for k in range(3))
+    v0, v1, v2 = pos[ib] - pos[ia], pos[ic] - pos[ia], p - pos[ia]
+    d00, d01, d11 = (v0 * v0).sum(1), (v0 * v1).sum(1), (v1 * v1).sum(1)
+    d20, d21 = (v2 * v0).sum(1), (v2 * v1).sum(1)
+    denom = d00 * d11 - d01 * d01
+    bv = (d11 * d20 - d01 * d21) / denom
+    bw = (d00 * d21 - d01 * d20) / denom
+    bu = 1 - bv - bw
+    uv = bu[:, None] * uvs[ia] + bv[:, None] * uvs[ib] + bw[:, None] * uvs[ic]
+    outside = ((uv < 0) | (uv > 1)).any(1)
+    uv = np.where(outside[:, None], uv - np.floor(uv), uv)
+    rect = world.material_data_buffer["albedo"][0].astype(np.float64)  # (u0, v0, su, sv)
+    au, av = rect[0] + uv[:, 0] * rect[2], rect[1] + uv[:, 1] * rect[3]
+    atlas = world.atlas.astype(np.float64)[..., :3] / 255.0
+    h, w = atlas.shape[:2]
+    px, py = au * w, av * h
+    fx, fy = px - np.floor(px), py - np.floor(py)
+    x0, x1 = np.floor(px).astype(int) % w, np.ceil(px).astype(int) % w
+    y0, y1 = np.floor(py).astype(int) % h, np.ceil(py).astype(int) % h
+    top = atlas[y0, x0] + (atlas[y0, x1] - atlas[y0, x0]) * fx[:, None]
+    bot = atlas[y1, x0] + (atlas[y1, x1] - atlas[y1, x0]) * fx[:, None]
+    out = top + (bot - top) * fy[:, None]
+    out[~hitmask] = np.nan
+    return out.reshape(height, width, 3)
+
+
 def constant_sky(value=SHELL_EMISSION, width=8, height=4):
     img = np.empty((height, width, 4), np.float32)
     img[..., :3] = value

@@ -10,6 +10,8 @@ What each case pins:
   procedural_sky        S1: the 12-step Rayleigh + Mie scattering of skybox.rs against a float64 numpy restatement
   flat_normal_map       H2: normal-map fetch, TBN, normalize — a flat map reproduces the diffuse-only closed form
   constant_textures     H3 / B1: albedo, roughness and metallic read through the atlas == the same constants as factors
+  albedo_texture        H1 / H3 on a NON-constant texture: (textured) / (white) per pixel == numpy restatement of
+                        barycentrics -> uv -> rect -> bilinear RGBA8 lookup at the primary hit
   diffuse_only          B2 diffuse branch, create_cartesian, cosine sampling, Fresnel, H1 interpolation:
                         L * albedo * E[1 - Schlick(h.v)] by quadrature
   mirror_limit          B2 specular branch (reflect, sample_ggx, D / G / pdf algebra): L * Schlick(n.v, f0)
@@ -159,6 +161,26 @@ def test_flat_normal_map_changes_nothing_but_the_normalisation(render):
     want = ka.diffuse_only_prediction(S, S, (0.18, 0.18, 0.18), ka.SHELL_EMISSION)
     err, npix = ka.relative_error_of_mean(img, want)
     assert np.isfinite(img).all() and npix > 400 and err.max() < 5e-3, err
+
+
+@pytest.mark.parametrize("render", BACKENDS)
+def test_albedo_texture_lookup_against_numpy(render):
+    """A smooth, NON-constant albedo texture: with the diffuse lobe only, every sample's radiance is proportional to the
+    albedo it looked up, so (textured render) / (white render, same seeds) is the footprint-averaged albedo per pixel —
+    compared with a float64 numpy restatement of hit point -> barycentrics -> uv -> rect -> bilinear RGBA8 lookup."""
+    cfg = helpers.config(S, S, 0, has_skybox=1, specular_weight_clamp=[0.0, 0.0])
+    seeds = helpers.seeds(S, S)
+    world = ka.gradient_albedo_sphere_world()
+    textured = render(world, cfg, seeds, 32, ka.constant_sky())
+    white = render(ka.sphere_only_world((1.0, 1.0, 1.0)), cfg, seeds, 32, ka.constant_sky())
+    want = ka.albedo_texture_prediction(world, S, S)
+    inside = np.isfinite(ka.sphere_pixel_cosines(S, S)) & np.isfinite(want).all(-1) & (white > 0).all(-1)
+    ratio = textured[inside] / white[inside]
+    err = np.abs(ratio - want[inside])
+    assert inside.sum() > 400 and want[inside][:, 0].std() > 0.05 and want[inside][:, 1].std() > 0.02  # the texture does vary across the sphere
+    # measured: 95th percentile 4.1e-4, mean 1.7e-3; the tail (max 0.19) is the uv seam of the sphere, where a pixel's
+    # jittered samples fall on both sides of a jump that its centre does not see
+    assert np.percentile(err, 95) < 3e-3 and err.mean() < 6e-3, (err.mean(), np.percentile(err, 95), err.max())
 
 
 @pytest.mark.parametrize("render", BACKENDS)
